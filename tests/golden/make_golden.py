@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""
+Generates ``tests/golden/*.npz`` by running the UNMODIFIED reference hot-path files from
+``/root/reference`` (through ``oracle/ref_loader.py``) on seeded synthetic inputs.
+
+Run in the build container only (the reference tree does not travel):
+    python tests/golden/make_golden.py
+Each fixture stores the case parameters, a SHA-256 of the regenerated inputs, and the
+reference's clm/slm.  Inputs are not stored: ``tests/golden_cases.py`` rebuilds them from
+the same seeds.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from oracle import ref_loader          # noqa: E402
+import golden_cases                    # noqa: E402
+
+
+def main():
+    ref = ref_loader.load()
+    outdir = os.path.dirname(os.path.abspath(__file__))
+    for name in golden_cases.CASES:
+        func, args, kwargs = golden_cases.build(name)
+        Y = getattr(ref, func)(*args, **kwargs)
+        path = os.path.join(outdir, name + '.npz')
+        np.savez_compressed(path, clm=Y.clm, slm=Y.slm, lmax=int(Y.lmax), mmax=int(Y.mmax),
+                            input_sha256=golden_cases.digest(args, kwargs), func=func,
+                            real_gravity_toolkit=bool(ref.real_gravity_toolkit))
+        print('%-28s %-22s max|clm|=%.3e  %s' % (name, func, np.abs(Y.clm).max(), Y.clm.shape))
+
+
+if __name__ == '__main__':
+    main()
