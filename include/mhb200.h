@@ -1,0 +1,142 @@
+/*
+ * mhb200.h -- C ABI of the B200-native fields -> Stokes hot path.
+ *
+ * Drop-in boundary for the three operators of tsutterley/model-harmonics
+ * (paths relative to the reference tree):
+ *   model_harmonics/gen_pressure_stokes.py:81-209    -> mhb200_pressure_stokes_f64
+ *   model_harmonics/gen_atmosphere_stokes.py:86-278  -> mhb200_atmosphere_stokes
+ *   model_harmonics/gen_point_pressure.py:64-194     -> mhb200_point_pressure_f64
+ * The reference has no FFI: its boundary is those three Python functions
+ * (model_harmonics/__init__.py:19-21).  The Python package model_harmonics_b200 keeps
+ * their signatures and binds this library with ctypes.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter comment says "host";
+ *   - all arithmetic is IEEE binary64; float32 is accepted only as an input
+ *     storage type for the 3-D cubes (converted exactly on load);
+ *   - outputs clm/slm are (nbatch, lmax+1, mmax+1) row-major, fully written
+ *     (zeros where m > l);
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); the
+ *     calls do not synchronise;
+ *   - return value: MHB200_OK or a negative MHB200_E* code;
+ *     mhb200_last_error() gives a thread-local message.
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef MHB200_H_
+#define MHB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHB200_OK            0
+#define MHB200_EINVAL       -1   /* bad argument */
+#define MHB200_ECUDA        -2   /* CUDA runtime error (see mhb200_last_error) */
+#define MHB200_EWORKSPACE   -3   /* workspace too small */
+#define MHB200_ENODEVICE    -4   /* no usable CUDA device */
+
+/* integration over pressure levels, gen_atmosphere_stokes.py:254-265 */
+#define MHB200_METHOD_BC05   0
+#define MHB200_METHOD_SW02   1
+
+/* storage type of the (level, lat, lon) cubes */
+#define MHB200_F64           0
+#define MHB200_F32           1
+
+typedef struct mhb200_plan mhb200_plan;
+
+/* library / device probe; returns MHB200_OK when device `device` is an sm_100 part */
+int mhb200_version(void);
+int mhb200_device_check(int device);
+const char* mhb200_last_error(void);
+
+/*
+ * Geometry plan: everything that depends only on (lon, lat, LMAX, MMAX, latitude
+ * weights).  Replaces the tables the reference rebuilds per call:
+ *   m_phi = exp(1j*m*phi)            gen_pressure_stokes.py:176-177
+ *   PLM   = plm_holmes(LMAX,cos(th)) gen_pressure_stokes.py:180-182 (here: only the
+ *           O(L^2) recursion multipliers and the O(nlat*M) u^m rescale factors are
+ *           stored; P_lm itself is generated on the fly inside the kernel)
+ *   plm*int_fact                     gen_pressure_stokes.py:186-188
+ * phi[nlon]      host  longitudes in radians exactly as the operator forms them
+ * costh[nlat]    host  cos(colatitude)
+ * int_fact[nlat] host  latitude integration weights (WEIGHT or sin(th)*dphi*dth)
+ */
+int mhb200_plan_create(mhb200_plan** plan, int device, int nlat, int nlon, int lmax, int mmax,
+                       const double* phi, const double* costh, const double* int_fact);
+int mhb200_plan_destroy(mhb200_plan* plan);
+
+/* bytes of device workspace a call with these sizes needs (0 on bad arguments) */
+size_t mhb200_grid_workspace_bytes(const mhb200_plan* plan, int nbatch, int nlev);
+
+/*
+ * gen_pressure_stokes.py:194-206.  For each of nbatch fields:
+ *   C_lm + i S_lm = dfactor[l] * sum_h w_h Plm(x_h) sum_p e^{i m phi_p} (P/G) (R/rad_e)^(l+2)
+ * P, G, R are addressed as base[t*stride[0] + h*stride[1] + p*stride[2]] (element strides;
+ * 0 broadcasts), which covers lat x lon, lon x lat, scalar and 1-element operands
+ * (gen_pressure_stokes.py:146-151).
+ * dfactor[lmax+1]  host
+ * plm_table        NULL (on-the-fly Holmes-Featherstone recursion) or a device table
+ *                  (nlat, lmax+1, mmax+1) row-major holding a caller-supplied PLM
+ */
+int mhb200_pressure_stokes_f64(const mhb200_plan* plan,
+                               const double* P, const int64_t P_stride[3],
+                               const double* G, const int64_t G_stride[3],
+                               const double* R, const int64_t R_stride[3],
+                               int nbatch, double rad_e, const double* dfactor,
+                               const double* plm_table,
+                               double* clm_out, double* slm_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * gen_atmosphere_stokes.py:217-275, geometry pre-pass and level integration fused.
+ * GPH, dP          (nbatch, nlev, nlat, nlon) cubes of type `dtype` (MHB200_F64/F32)
+ * field_scale      host, NULL or 2*nbatch doubles (sg_t, sp_t): field t is
+ *                  (sg_t*GPH, sp_t*dP) formed on load -- lets a batch share one base cube
+ *                  (batch_stride 0)
+ * batch_stride     elements between consecutive fields of GPH/dP (0 = shared cube)
+ * geoid            (nlat, nlon) or NULL for 0; geoid_stride = {lat, lon} element strides
+ * ring_tab         device, 9*nlat doubles built on the host from colatitude exactly as the
+ *                  reference forms them: [0]=1-0.002644cos2t [1]=(1-0.0089cos2t)/6.245e6
+ *                  [2]=N(t) [3]=N(t)(1-e^2) [4]=sin t [5]=cos t [6]=gs(t)
+ *                  [7]=2(1.006803-0.06706cos^2 t) [8]=unused
+ * lon_tab          device, 2*nlon doubles: cos(phi), sin(phi)
+ * rad_e            datum(ELLIPSOID).rad_e [m]
+ */
+int mhb200_atmosphere_stokes(const mhb200_plan* plan, int dtype,
+                             const void* GPH, const void* dP, int64_t batch_stride,
+                             const double* field_scale,
+                             const double* geoid, const int64_t geoid_stride[2],
+                             const double* ring_tab, const double* lon_tab,
+                             int nlev, int nbatch, int method, double rad_e,
+                             const double* dfactor, const double* plm_table,
+                             double* clm_out, double* slm_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * gen_point_pressure.py:126-154,160-194.  Scattered points with disc areas:
+ *   C_lm + i S_lm = dfactor[l] * sum_p Pdisc_l(alpha_p) (P/G)_p (R_p/rad_e)^(l+2) Plm(cos th_p) e^{i m phi_p}
+ * phi, theta, area are (npts) device arrays; P is (nbatch, npts); G and R are addressed
+ * with an element stride (0 broadcasts a 1-element operand).  dfactor (host) already holds
+ * 4*pi*mmwe/(1+2l).
+ */
+size_t mhb200_points_workspace_bytes(int64_t npts, int nbatch, int lmax, int mmax);
+int mhb200_point_pressure_f64(int device, const double* P, const double* G, int64_t G_stride,
+                              const double* R, int64_t R_stride,
+                              const double* phi, const double* theta, const double* area,
+                              int64_t npts, int nbatch, int lmax, int mmax,
+                              double rad_e, const double* dfactor,
+                              double* clm_out, double* slm_out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* counters for bench.py: kernels launched by this library since load (all threads) */
+uint64_t mhb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHB200_H_ */

@@ -1,0 +1,871 @@
+// Gridded fields -> Stokes coefficients on B200 (sm_100a).
+//
+// Replaces the hot loops of the reference (paths relative to the reference tree):
+//   model_harmonics/gen_pressure_stokes.py:194-206      per-degree power pass + complex einsum
+//   model_harmonics/gen_atmosphere_stokes.py:217-275    geometry pre-pass, level loop, einsum
+// and the third-party gravity_toolkit.plm_holmes table they consume
+// (gen_pressure_stokes.py:180-188), which is regenerated on the fly here.
+//
+// Math, per field:
+//   C_lm + i S_lm = D_l * sum_h w_h Plm(x_h) * sum_p e^{i m phi_p} xi_l(h,p)
+// One latitude ring h at a time, the inner sum is a dense real contraction
+//   Dring[2(M+1) x (L+1)] = Trig[2(M+1) x nlon] * B_h[nlon x (L+1)],  B_h[p,l] = xi_l(h,p)
+// done with DMMA m8n8k4 tiles; B_h is *generated* in shared memory (never in HBM):
+//   pressure  : (P/G) (R/rad_e)^(l+2), running product in l
+//   atmosphere: sum over levels of (dp/gamma)(R/rad_e)^(l+2), geometry fused, one pass over
+//               the (level,lat,lon) cubes, coalesced along lon
+// then C += w_h Plm(x_h) o Dring with Plm from a per-ring Holmes-Featherstone recursion.
+//
+// Kernel shape: persistent CTAs (one per SM, 256 threads), static schedule of
+// (field, degree-block, order-block, ring-range) segments built on the host so every CTA
+// gets equal fp64-pipe work; each segment ends in a private partial-sum slot and a second
+// kernel reduces the slots in fixed order (bit-reproducible, no fp64 atomics).
+// DFMA and DMMA share one fp64 pipe on B200 (measured: profiles/r01_fp64_peaks.jsonl), so the
+// CTA alternates a produce phase (all warps DFMA) and a contraction phase (all warps DMMA)
+// rather than specialising warps.
+#include "../../include/mhb200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace mhb {
+
+constexpr int NT = 256;           // threads per CTA
+constexpr int LBLK = 64;          // degrees per block
+constexpr int MBLK = 64;          // orders per block
+constexpr int KC_MAX = 128;       // longitudes per chunk (upper bound)
+constexpr int KS_MAX = KC_MAX / 4;
+constexpr int PLM_PITCH = 65;
+constexpr int CS_ROWS = 36;       // per-thread accumulators kept in shared memory
+constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
+constexpr int DF_MAX = 448;
+constexpr size_t SMEM_BYTES = (size_t)(KS_MAX * 256 + CS_ROWS * NT + MBLK * PLM_PITCH) * sizeof(double);
+
+enum Mode { MODE_PRESSURE = 0, MODE_ATM_BC05 = 1, MODE_ATM_SW02 = 2 };
+
+struct Segment {
+  int t, lb, mb, h0, h1, pad;
+};
+
+struct GridParams {
+  int nlat, nlon, lmax, mmax, Mpad, kc, nchunks, nks_total;
+  const double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
+  const double* plm_table;
+  const Segment* segs;
+  const int* cta_seg_begin;
+  double* slots;
+  // pressure
+  const double *P, *G, *R;
+  long long Ps[3], Gs[3], Rs[3];
+  double rad_e;
+  // atmosphere
+  const void *GPH, *dP;
+  long long batch_stride;
+  const double* field_scale;
+  const double* geoid;
+  long long geo_s0, geo_s1;
+  const double *ring_tab, *lon_tab;
+  int nlev;
+};
+
+struct ReduceParams {
+  int lmax, mmax, nmb, ntiles;
+  const int* tile_slot_begin;   // [nbatch*ntiles + 1]
+  const int* lb_first_tile;     // [nlb]
+  const double* slots;
+  const double* dfactor_dev;    // used when lmax+1 > DF_MAX
+  double *clm, *slm;
+  double dfactor[DF_MAX];       // degree factors travel as kernel parameters
+};
+
+// ---------------------------------------------------------------------------------------
+// Holmes-Featherstone column recursion for one ring and one (degree-block, order-block) tile.
+// Thread m_local computes order m = 64*mb + m_local for degrees m..lend and stores the
+// weighted values w_h * Plm(x_h) for degrees in the block.  Operation order mirrors
+// gravity_toolkit.plm_holmes (oracle/gravtk_standin.py): p_l = (x*f1)*p_{l-1} - f2*p_{l-2},
+// unfused, then *rescale (= u^m / 1e-280), then *int_fact.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void legendre_ring(const GridParams& p, int h, int lb, int mb, int m_local,
+                                              double* plm_s) {
+  const int m = mb * MBLK + m_local;
+  const int lbase = lb * LBLK;
+  const int lend = min(lbase + LBLK - 1, p.lmax);
+  double* row = plm_s + m_local * PLM_PITCH;
+  if (p.plm_table != nullptr) {
+    const double wh = p.w[h];
+    const double* tab = p.plm_table + (size_t)h * (p.lmax + 1) * (p.mmax + 1);
+    for (int j = 0; j < LBLK; ++j) {
+      const int l = lbase + j;
+      double v = 0.0;
+      if (l <= p.lmax && m <= p.mmax && m <= l) v = __dmul_rn(tab[(size_t)l * (p.mmax + 1) + m], wh);
+      row[j] = v;
+    }
+    return;
+  }
+  if (m > p.mmax || m > lend) {
+    for (int j = 0; j < LBLK; ++j) row[j] = 0.0;
+    return;
+  }
+  const double x = p.x[h];
+  const double wh = p.w[h];
+  const double rs = p.rescale[(size_t)h * p.Mpad + m];
+  // zero the part of the block below the diagonal and above lmax
+  for (int j = 0; j < LBLK; ++j) {
+    const int l = lbase + j;
+    if (l < m || l > p.lmax) row[j] = 0.0;
+  }
+  double p2 = p.pmm[m];  // degree m (sectoral), scaled
+  if (m >= lbase) row[m - lbase] = __dmul_rn(__dmul_rn(p2, rs), wh);
+  if (m + 1 > lend) return;
+  double p1 = __dmul_rn(__dmul_rn(x, p.sq[m]), p2);  // degree m+1
+  if (m + 1 >= lbase) row[m + 1 - lbase] = __dmul_rn(__dmul_rn(p1, rs), wh);
+  const double* f1 = p.f1 + m;
+  const double* f2 = p.f2 + m;
+  for (int l = m + 2; l <= lend; ++l) {
+    const double a = __ldg(f1 + (size_t)l * p.Mpad);
+    const double b = __ldg(f2 + (size_t)l * p.Mpad);
+    const double pl = __dsub_rn(__dmul_rn(__dmul_rn(x, a), p1), __dmul_rn(b, p2));
+    p2 = p1;
+    p1 = pl;
+    if (l >= lbase) row[l - lbase] = __dmul_rn(__dmul_rn(pl, rs), wh);
+  }
+}
+
+// B-fragment slot of element (l_local, column) inside the chunk buffer.  Fragment-major:
+// [kstep][degree-tile][32 slots]; the row is rotated by kstep so that both the producer's
+// stores (16 columns x fixed degree per half-warp) and the consumer's fragment loads are
+// bank-conflict free.
+__device__ __forceinline__ int bs_index(int l_local, int col) {
+  const int ks = col >> 2, c = col & 3;
+  return ((ks * 8 + (l_local >> 3)) << 5) + ((((l_local & 7) + ks) & 7) << 2) + c;
+}
+
+// ---------------------------------------------------------------------------------------
+// Produce phase, pressure:  B[p,l] = (P/G) * (R/rad_e)^(l+2)   (gen_pressure_stokes.py:200)
+// A column is shared by the lane pair (lane, lane^16): each handles 32 of the 64 degrees.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void produce_pressure(const GridParams& p, int t, int h, int lb, int chunk,
+                                                 double* Bs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = warp * 16 + (lane & 15), half = lane >> 4;
+  if (col >= p.kc) return;
+  const int pcol = chunk * p.kc + col;
+  double f = 0.0, r = 1.0;
+  if (pcol < p.nlon) {
+    const double Pv = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pcol * p.Ps[2]);
+    const double Gv = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pcol * p.Gs[2]);
+    const double Rv = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pcol * p.Rs[2]);
+    f = Pv / Gv;
+    r = Rv / p.rad_e;
+  }
+  const int l0 = 32 * half;
+  double val = f * ipow(r, lb * LBLK + l0 + 2);
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    Bs[bs_index(l0 + j, col)] = val;
+    val *= r;
+  }
+}
+
+// One level's contribution to the 32 degrees this thread owns:  acc[j] += u * r^j.
+// Stride-8 scheme: 7 powers + per stride one add, seven FMAs and one multiply
+// (1.25 fp64-pipe slots per degree instead of 2 for "acc += t; t *= r").
+__device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, double r, int half) {
+  const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
+  const double r5 = r4 * r, r6 = r4 * r2, r7 = r4 * r3, r8 = r4 * r4;
+  const double r16 = r8 * r8, r32 = r16 * r16;
+  u *= (half ? r32 : 1.0);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    acc[8 * s + 0] += u;
+    acc[8 * s + 1] = fma(u, r, acc[8 * s + 1]);
+    acc[8 * s + 2] = fma(u, r2, acc[8 * s + 2]);
+    acc[8 * s + 3] = fma(u, r3, acc[8 * s + 3]);
+    acc[8 * s + 4] = fma(u, r4, acc[8 * s + 4]);
+    acc[8 * s + 5] = fma(u, r5, acc[8 * s + 5]);
+    acc[8 * s + 6] = fma(u, r6, acc[8 * s + 6]);
+    acc[8 * s + 7] = fma(u, r7, acc[8 * s + 7]);
+    u *= r8;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Produce phase, atmosphere (gen_atmosphere_stokes.py:217-265 fused):
+//   B[p,l] = - sum_k (dp_k/gamma_k) (R_k/rad_e)^(l+2)                      BC05
+//   B[p,l] = - sum_k (dp_k/g0) (rad_e/(rad_e-GPH_k) + GEOID/rad_e)^(l+4)   SW02
+// (the minus sign is the reference's einsum(m_phi, -pfactor), :270).
+// Lane pair (lane, lane^16) shares a column; the pair splits the levels for the geometry
+// (even/odd level) and the degrees for the accumulation (lower/upper 32).
+// ---------------------------------------------------------------------------------------
+template <int MODE, typename Tin>
+__device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, int h, int lb, int chunk,
+                                                   double* Bs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = warp * 16 + (lane & 15), half = lane >> 4;
+  const int pcol = chunk * p.kc + col;
+  const bool active = (col < p.kc) && (pcol < p.nlon);
+  const size_t lev_stride = (size_t)p.nlat * p.nlon;
+  const int pc = active ? pcol : 0;
+  const Tin* zp = (const Tin*)p.GPH + (size_t)t * p.batch_stride + (size_t)h * p.nlon + pc;
+  const Tin* dp = (const Tin*)p.dP + (size_t)t * p.batch_stride + (size_t)h * p.nlon + pc;
+  double sg = 1.0, sp = 1.0;
+  if (p.field_scale != nullptr) {
+    sg = p.field_scale[2 * t];
+    sp = p.field_scale[2 * t + 1];
+  }
+  const double geo = (p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + pc * p.geo_s1) : 0.0;
+  const double inv_rad = 1.0 / p.rad_e;
+  // ring (colatitude-only) and longitude-only factors, built on the host
+  const double a1 = p.ring_tab[0 * p.nlat + h], a2 = p.ring_tab[1 * p.nlat + h];
+  const double NG = p.ring_tab[2 * p.nlat + h] + geo;     // (N + GEOID)
+  const double NG1 = p.ring_tab[3 * p.nlat + h] + geo;    // (N(1-e^2) + GEOID)
+  const double st = p.ring_tab[4 * p.nlat + h], ct = p.ring_tab[5 * p.nlat + h];
+  const double gs = p.ring_tab[6 * p.nlat + h], c1 = p.ring_tab[7 * p.nlat + h];
+  const double cphi = p.lon_tab[pc], sphi = p.lon_tab[p.nlon + pc];
+  const double geo_over = geo / p.rad_e;
+  const double g0 = 9.80665;
+
+  double acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+
+  // software-pipelined level loop: the pair handles levels (k0, k0+1) per iteration
+  const int nlev = p.nlev;
+  double z_n = 0.0, d_n = 0.0;
+  {
+    const int k = half;
+    if (active && k < nlev) {
+      z_n = ld_as_double(zp + k * lev_stride);
+      d_n = ld_as_double(dp + k * lev_stride);
+    }
+  }
+  for (int k0 = 0; k0 < nlev; k0 += 2) {
+    const double z = sg * z_n, dpv = sp * d_n;
+    const bool valid = active && (k0 + half < nlev);
+    {
+      const int k = k0 + 2 + half;
+      z_n = 0.0;
+      d_n = 0.0;
+      if (active && k < nlev) {
+        z_n = ld_as_double(zp + k * lev_stride);
+        d_n = ld_as_double(dp + k * lev_stride);
+      }
+    }
+    double u0, r;
+    if (MODE == MODE_ATM_BC05) {
+      // orthometric height (List 1958), :222-224
+      const double H = a1 * z + a2 * (z * z);
+      const double A = NG + H, B = NG1 + H;
+      const double As = A * st;
+      const double X = As * cphi, Y = As * sphi, Z = B * ct;
+      const double R = sqrt(fma(Z, Z, fma(Y, Y, X * X)));      // :226-230
+      r = R * inv_rad;
+      const double hr = H * inv_rad;
+      const double gam = gs * fma(3.0 * hr, hr, fma(-c1, hr, 1.0));   // :232-238
+      const double q = dpv / gam;
+      u0 = -(q * r) * r;
+    } else {
+      r = p.rad_e / (p.rad_e - z) + geo_over;                  // :258-260
+      const double q = dpv / g0;
+      const double r2 = r * r;
+      u0 = -(q * r2) * r2;
+    }
+    if (lb > 0) u0 *= ipow(r, lb * LBLK);
+    if (!valid) {
+      u0 = 0.0;
+      r = 1.0;
+    }
+    const double pu = __shfl_xor_sync(0xffffffffu, u0, 16);
+    const double pr = __shfl_xor_sync(0xffffffffu, r, 16);
+    // even level first, then odd, for both halves (fixed summation order)
+    accumulate_level(acc, half ? pu : u0, half ? pr : r, half);
+    accumulate_level(acc, half ? u0 : pu, half ? r : pr, half);
+  }
+  if (col < p.kc) {
+    const int l0 = 32 * half;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) Bs[bs_index(l0 + j, col)] = acc[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// One segment: rings h0..h1 of tile (lb, mb) of field t.
+// DIAG tile (lb == mb): only 8x8 sub-tiles with degree-tile >= order-tile are needed (36 of
+// 64).  Warp w: order groups gA = w&3 and gB = 7-gA (9 sub-tile pairs, balanced), k-steps of
+// parity w>>2.  FULL tile: warp w owns order group w, all 8 degree tiles, every k-step.
+// ---------------------------------------------------------------------------------------
+template <int MODE, typename Tin, bool DIAG>
+__device__ __forceinline__ void run_segment(const GridParams& p, const Segment seg, int slot_index,
+                                            double* Bs, double* Cs, double* plm_s) {
+  constexpr int NP = DIAG ? 9 : 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gA = DIAG ? (warp & 3) : warp;
+  const int gB = DIAG ? (7 - gA) : warp;
+  const int nA = DIAG ? (8 - gA) : 8;
+  const int kpar = DIAG ? (warp >> 2) : 0;
+  const int kstep = DIAG ? 2 : 1;
+  const int nksc = p.kc >> 2;
+
+  int lt[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) lt[j] = DIAG ? ((j < nA) ? (gA + j) : (j - 1)) : j;
+
+#pragma unroll
+  for (int i = 0; i < NP * 4; ++i) Cs[i * NT + tid] = 0.0;
+
+  for (int h = seg.h0; h < seg.h1; ++h) {
+    if (tid < MBLK) legendre_ring(p, h, seg.lb, seg.mb, tid, plm_s);
+
+    double acc[NP][2][2];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
+
+    for (int chunk = 0; chunk < p.nchunks; ++chunk) {
+      if (MODE == MODE_PRESSURE)
+        produce_pressure(p, seg.t, h, seg.lb, chunk, Bs);
+      else
+        produce_atmosphere<MODE, Tin>(p, seg.t, h, seg.lb, chunk, Bs);
+      __syncthreads();
+
+      // contraction over the chunk's longitudes; trig fragments straight from L2 (fragment-major
+      // table: one coalesced 256-byte load per fragment), B fragments from shared memory
+      const double* Ablk = p.trig + ((size_t)(seg.mb * p.nks_total + chunk * nksc) * 16) * 32 + lane;
+      int ks = kpar;
+      double aAc = 0, aAs = 0, aBc = 0, aBs = 0;
+      if (ks < nksc) {
+        const double* a = Ablk + (size_t)ks * 512;
+        aAc = __ldg(a + (gA * 2) * 32);
+        aAs = __ldg(a + (gA * 2 + 1) * 32);
+        if (DIAG) {
+          aBc = __ldg(a + (gB * 2) * 32);
+          aBs = __ldg(a + (gB * 2 + 1) * 32);
+        }
+      }
+      for (; ks < nksc; ks += kstep) {
+        const double cAc = aAc, cAs = aAs, cBc = aBc, cBs = aBs;
+        const int kn = ks + kstep;
+        if (kn < nksc) {
+          const double* a = Ablk + (size_t)kn * 512;
+          aAc = __ldg(a + (gA * 2) * 32);
+          aAs = __ldg(a + (gA * 2 + 1) * 32);
+          if (DIAG) {
+            aBc = __ldg(a + (gB * 2) * 32);
+            aBs = __ldg(a + (gB * 2 + 1) * 32);
+          }
+        }
+        const double* Bk = Bs + ks * 256 + ((((lane >> 2) + ks) & 7) << 2) + (lane & 3);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const double b = Bk[lt[j] * 32];
+          const bool first = (!DIAG) || (j < nA);
+          dmma884(acc[j][0][0], acc[j][0][1], first ? cAc : cBc, b);
+          dmma884(acc[j][1][0], acc[j][1][1], first ? cAs : cBs, b);
+        }
+      }
+      __syncthreads();
+    }
+
+    // ring epilogue: C += (w_h Plm) o Dring
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int g = ((!DIAG) || (j < nA)) ? gA : gB;
+      const int m_local = g * 8 + (lane >> 2);
+      const int l_local = lt[j] * 8 + 2 * (lane & 3);
+      const double w0 = plm_s[m_local * PLM_PITCH + l_local];
+      const double w1 = plm_s[m_local * PLM_PITCH + l_local + 1];
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs) {
+        double* c = Cs + ((j * 2 + cs) * 2) * NT + tid;
+        c[0] = fma(w0, acc[j][cs][0], c[0]);
+        c[NT] = fma(w1, acc[j][cs][1], c[NT]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // write the segment's partial sums: slot[cs][l_local][m_local]
+  double* slot = p.slots + (size_t)slot_index * SLOT_DOUBLES;
+  if (!DIAG || tid < 128) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int g = ((!DIAG) || (j < nA)) ? gA : gB;
+      const int m_local = g * 8 + (lane >> 2);
+      const int l_local = lt[j] * 8 + 2 * (lane & 3);
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int row = ((j * 2 + cs) * 2 + e) * NT;
+          double v = Cs[row + tid];
+          if (DIAG) v += Cs[row + tid + 128];   // the two k-parities
+          slot[(cs * LBLK + l_local + e) * MBLK + m_local] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int MODE, typename Tin>
+__global__ void __launch_bounds__(NT, 1) stokes_ring_kernel(const GridParams p) {
+  extern __shared__ double smem[];
+  double* Bs = smem;
+  double* Cs = Bs + KS_MAX * 256;
+  double* plm_s = Cs + CS_ROWS * NT;
+  const int sb = p.cta_seg_begin[blockIdx.x], se = p.cta_seg_begin[blockIdx.x + 1];
+  for (int s = sb; s < se; ++s) {
+    const Segment seg = p.segs[s];
+    if (seg.lb == seg.mb)
+      run_segment<MODE, Tin, true>(p, seg, s, Bs, Cs, plm_s);
+    else
+      run_segment<MODE, Tin, false>(p, seg, s, Bs, Cs, plm_s);
+  }
+}
+
+// Fixed-order reduction of the partial slots + degree factors (gen_pressure_stokes.py:205-206).
+// grid (lmax+1, nbatch), one thread per order.
+__global__ void stokes_reduce_kernel(const __grid_constant__ ReduceParams q) {
+  const int l = blockIdx.x, t = blockIdx.y;
+  const int ncol = q.mmax + 1;
+  const double df = (q.dfactor_dev != nullptr) ? q.dfactor_dev[l] : q.dfactor[l];
+  const int lb = l / LBLK, l_local = l % LBLK;
+  for (int m = threadIdx.x; m < ncol; m += blockDim.x) {
+    double c = 0.0, s = 0.0;
+    if (m <= l) {
+      const int mb = m / MBLK, m_local = m % MBLK;
+      const int tile = t * q.ntiles + q.lb_first_tile[lb] + mb;
+      const int b = q.tile_slot_begin[tile], e = q.tile_slot_begin[tile + 1];
+      for (int k = b; k < e; ++k) {
+        const double* slot = q.slots + (size_t)k * SLOT_DOUBLES;
+        c += slot[(l_local)*MBLK + m_local];
+        s += slot[(LBLK + l_local) * MBLK + m_local];
+      }
+      c *= df;
+      s *= df;
+    }
+    const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
+    q.clm[o] = c;
+    q.slm[o] = s;
+  }
+}
+
+}  // namespace mhb
+
+// =========================================================================================
+// host side: plan, schedule, entry points
+// =========================================================================================
+using namespace mhb;
+
+struct Schedule {
+  int nbatch = -1, nlev = -1, mode = -1;
+  int ncta = 0, nseg = 0;
+  Segment* segs_dev = nullptr;
+  int* cta_seg_begin_dev = nullptr;
+  int* tile_slot_begin_dev = nullptr;
+};
+
+struct mhb200_plan {
+  int device, nlat, nlon, lmax, mmax;
+  int nlb, nmb, Mpad, ntiles;
+  int kc, nchunks, nks_total, num_sms;
+  double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
+  int* lb_first_tile_dev;
+  std::vector<int> lb_first_tile;
+  // per-call staging (dfactor, field scales), grown on demand
+  double* stage_dev;
+  size_t stage_doubles;
+  size_t stage_reserved;   // doubles at the front of the staging buffer used by field scales
+  std::mutex mu;
+  Schedule sched;
+};
+
+namespace {
+
+template <typename T>
+int upload(T** dev, const std::vector<T>& host) {
+  MHB_CUDA(cudaMalloc((void**)dev, std::max<size_t>(host.size(), 1) * sizeof(T)));
+  if (!host.empty()) MHB_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MHB200_OK;
+}
+
+// fp64-pipe cost (arbitrary units per longitude) of one ring of one tile
+double ring_cost(bool diag, int mode, int nlev) {
+  const double mma = diag ? 4608.0 : 8192.0;
+  const double prod = (mode == MODE_PRESSURE) ? 90.0 : (double)nlev * 136.0;
+  return mma + prod;
+}
+
+int build_schedule(mhb200_plan* pl, int nbatch, int nlev, int mode) {
+  Schedule& sc = pl->sched;
+  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode) return MHB200_OK;
+  if (sc.segs_dev) cudaFree(sc.segs_dev);
+  if (sc.cta_seg_begin_dev) cudaFree(sc.cta_seg_begin_dev);
+  if (sc.tile_slot_begin_dev) cudaFree(sc.tile_slot_begin_dev);
+  sc = Schedule();
+  // linearised work: (field, tile, ring) with per-ring cost
+  struct Tile { int lb, mb; double c; };
+  std::vector<Tile> tiles;
+  for (int lb = 0; lb < pl->nlb; ++lb)
+    for (int mb = 0; mb <= std::min(lb, pl->nmb - 1); ++mb)
+      tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev)});
+  double per_field = 0.0;
+  for (auto& tl : tiles) per_field += tl.c * pl->nlat;
+  const double total = per_field * nbatch;
+  const long long units = (long long)nbatch * (long long)tiles.size() * pl->nlat;
+  const int ncta = (int)std::min<long long>(pl->num_sms, units);
+  std::vector<Segment> segs;
+  std::vector<int> cta_begin(ncta + 1, 0);
+  std::vector<int> tile_slot_begin((size_t)nbatch * tiles.size() + 1, 0);
+  double done = 0.0;
+  int cta = 0;
+  for (int t = 0; t < nbatch; ++t) {
+    for (size_t ti = 0; ti < tiles.size(); ++ti) {
+      tile_slot_begin[(size_t)t * tiles.size() + ti] = (int)segs.size();
+      const double c = tiles[ti].c;
+      int h = 0;
+      while (h < pl->nlat) {
+        // rings the current CTA can still take before its cost boundary
+        const double boundary = total * (double)(cta + 1) / (double)ncta;
+        int take = (int)std::floor((boundary - done) / c + 0.5);
+        if (cta == ncta - 1) take = pl->nlat - h;
+        take = std::max(0, std::min(take, pl->nlat - h));
+        if (take > 0) {
+          segs.push_back({t, tiles[ti].lb, tiles[ti].mb, h, h + take, 0});
+          h += take;
+          done += take * c;
+        }
+        if (h < pl->nlat && cta < ncta - 1) {   // this CTA is full: move to the next one
+          ++cta;
+          cta_begin[cta] = (int)segs.size();
+        }
+      }
+      // tile finished exactly at (or past) the CTA's boundary: next tile starts on a new CTA
+      if (cta < ncta - 1 && done >= total * (double)(cta + 1) / (double)ncta - 0.5 * c) {
+        ++cta;
+        cta_begin[cta] = (int)segs.size();
+      }
+    }
+  }
+  for (int c = cta + 1; c <= ncta; ++c) cta_begin[c] = (int)segs.size();
+  tile_slot_begin.back() = (int)segs.size();
+  sc.ncta = ncta;
+  sc.nseg = (int)segs.size();
+  int rc;
+  if ((rc = upload(&sc.segs_dev, segs)) != MHB200_OK) return rc;
+  if ((rc = upload(&sc.cta_seg_begin_dev, cta_begin)) != MHB200_OK) return rc;
+  if ((rc = upload(&sc.tile_slot_begin_dev, tile_slot_begin)) != MHB200_OK) return rc;
+  sc.nbatch = nbatch;
+  sc.nlev = nlev;
+  sc.mode = mode;
+  return MHB200_OK;
+}
+
+size_t max_segments(const mhb200_plan* pl, int nbatch) {
+  // every (field, tile) contributes at least one segment and every CTA boundary at most one more
+  return (size_t)nbatch * pl->ntiles + pl->num_sms + 1;
+}
+
+int stage(mhb200_plan* pl, const double* host, size_t n, size_t offset, cudaStream_t st) {
+  if (offset + n > pl->stage_doubles) {
+    set_err("internal: staging buffer too small");
+    return MHB200_EINVAL;
+  }
+  MHB_CUDA(cudaMemcpyAsync(pl->stage_dev + offset, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  return MHB200_OK;
+}
+
+int ensure_stage(mhb200_plan* pl, size_t n) {
+  if (n <= pl->stage_doubles) return MHB200_OK;
+  if (pl->stage_dev) {
+    MHB_CUDA(cudaDeviceSynchronize());
+    cudaFree(pl->stage_dev);
+    pl->stage_dev = nullptr;
+    pl->stage_doubles = 0;
+  }
+  MHB_CUDA(cudaMalloc((void**)&pl->stage_dev, n * sizeof(double)));
+  pl->stage_doubles = n;
+  return MHB200_OK;
+}
+
+template <int MODE, typename Tin>
+int launch_ring(const GridParams& gp, int ncta, cudaStream_t st) {
+  auto kern = stokes_ring_kernel<MODE, Tin>;
+  MHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  kern<<<ncta, NT, SMEM_BYTES, st>>>(gp);
+  g_launches.fetch_add(1);
+  MHB_CUDA(cudaGetLastError());
+  return MHB200_OK;
+}
+
+int finish_reduce(mhb200_plan* pl, const double* dfactor, int nbatch, double* slots, double* clm, double* slm,
+                  cudaStream_t st) {
+  ReduceParams q;
+  q.dfactor_dev = nullptr;
+  if (pl->lmax + 1 <= DF_MAX) {
+    for (int l = 0; l <= pl->lmax; ++l) q.dfactor[l] = dfactor[l];
+  } else {
+    int rc;
+    if ((rc = ensure_stage(pl, (size_t)pl->lmax + 1 + pl->stage_reserved)) != MHB200_OK) return rc;
+    if ((rc = stage(pl, dfactor, (size_t)pl->lmax + 1, pl->stage_reserved, st)) != MHB200_OK) return rc;
+    q.dfactor_dev = pl->stage_dev + pl->stage_reserved;
+  }
+  q.lmax = pl->lmax;
+  q.mmax = pl->mmax;
+  q.nmb = pl->nmb;
+  q.ntiles = pl->ntiles;
+  q.tile_slot_begin = pl->sched.tile_slot_begin_dev;
+  q.lb_first_tile = pl->lb_first_tile_dev;
+  q.slots = slots;
+  q.clm = clm;
+  q.slm = slm;
+  dim3 grid(pl->lmax + 1, nbatch);
+  stokes_reduce_kernel<<<grid, 64, 0, st>>>(q);
+  g_launches.fetch_add(1);
+  MHB_CUDA(cudaGetLastError());
+  return MHB200_OK;
+}
+
+void fill_plan_params(const mhb200_plan* pl, GridParams& gp) {
+  memset(&gp, 0, sizeof(gp));
+  gp.nlat = pl->nlat;
+  gp.nlon = pl->nlon;
+  gp.lmax = pl->lmax;
+  gp.mmax = pl->mmax;
+  gp.Mpad = pl->Mpad;
+  gp.kc = pl->kc;
+  gp.nchunks = pl->nchunks;
+  gp.nks_total = pl->nks_total;
+  gp.trig = pl->trig;
+  gp.f1 = pl->f1;
+  gp.f2 = pl->f2;
+  gp.pmm = pl->pmm;
+  gp.sq = pl->sq;
+  gp.rescale = pl->rescale;
+  gp.x = pl->x;
+  gp.w = pl->w;
+  gp.segs = pl->sched.segs_dev;
+  gp.cta_seg_begin = pl->sched.cta_seg_begin_dev;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lmax, int mmax,
+                       const double* phi, const double* costh, const double* int_fact) {
+  if (!out || nlat < 1 || nlon < 1 || lmax < 0 || mmax < 0 || mmax > lmax || !phi || !costh || !int_fact) {
+    set_err("mhb200_plan_create: bad argument");
+    return MHB200_EINVAL;
+  }
+  int rc = mhb200_device_check(device);
+  if (rc != MHB200_OK) return rc;
+  MHB_CUDA(cudaSetDevice(device));
+  mhb200_plan* pl = new mhb200_plan();
+  pl->device = device;
+  pl->nlat = nlat;
+  pl->nlon = nlon;
+  pl->lmax = lmax;
+  pl->mmax = mmax;
+  pl->nlb = (lmax + LBLK) / LBLK;
+  pl->nmb = (mmax + MBLK) / MBLK;
+  pl->Mpad = pl->nmb * MBLK;
+  pl->nchunks = (nlon + KC_MAX - 1) / KC_MAX;
+  pl->kc = (((nlon + pl->nchunks - 1) / pl->nchunks) + 7) / 8 * 8;
+  pl->nks_total = pl->nchunks * (pl->kc / 4);
+  pl->stage_dev = nullptr;
+  pl->stage_doubles = 0;
+  pl->stage_reserved = 0;
+  cudaDeviceProp prop;
+  MHB_CUDA(cudaGetDeviceProperties(&prop, device));
+  pl->num_sms = prop.multiProcessorCount;
+  pl->lb_first_tile.resize(pl->nlb);
+  int nt = 0;
+  for (int lb = 0; lb < pl->nlb; ++lb) {
+    pl->lb_first_tile[lb] = nt;
+    nt += std::min(lb + 1, pl->nmb);
+  }
+  pl->ntiles = nt;
+
+  // trig table, fragment-major [mb][kstep][16 row tiles][32 lanes]  (m_phi, gen_pressure_stokes.py:176-177)
+  const int npad = pl->nks_total * 4;
+  std::vector<double> trig((size_t)pl->nmb * pl->nks_total * 512, 0.0);
+  for (int mb = 0; mb < pl->nmb; ++mb)
+    for (int ks = 0; ks < pl->nks_total; ++ks)
+      for (int g = 0; g < 8; ++g)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int m = mb * MBLK + g * 8 + (lane >> 2);
+          const int p = ks * 4 + (lane & 3);
+          if (m > mmax || p >= nlon || p >= npad) continue;
+          const double arg = (double)m * phi[p];
+          const size_t base = (((size_t)mb * pl->nks_total + ks) * 16 + g * 2) * 32 + lane;
+          trig[base] = cos(arg);
+          trig[base + 32] = sin(arg);
+        }
+  // Holmes-Featherstone multipliers [(lmax+1)][Mpad], sectoral seeds and sqrt(2m+3)
+  const int Mpad = pl->Mpad;
+  std::vector<double> f1((size_t)(lmax + 1) * Mpad, 0.0), f2((size_t)(lmax + 1) * Mpad, 0.0);
+  for (int l = 2; l <= lmax; ++l) {
+    const double dl = (double)l;
+    f1[(size_t)l * Mpad] = sqrt(2.0 * dl - 1.0) * sqrt(2.0 * dl + 1.0) / dl;
+    f2[(size_t)l * Mpad] = (dl - 1.0) * sqrt(2.0 * dl + 1.0) / (sqrt(2.0 * dl - 3.0) * dl);
+    for (int m = 1; m <= std::min(l - 2, mmax); ++m) {
+      const double dm = (double)m;
+      f1[(size_t)l * Mpad + m] = sqrt(2.0 * dl + 1.0) * sqrt(2.0 * dl - 1.0) / (sqrt(dl + dm) * sqrt(dl - dm));
+      f2[(size_t)l * Mpad + m] = sqrt(2.0 * dl + 1.0) * sqrt(dl - dm - 1.0) * sqrt(dl + dm - 1.0) /
+                                 (sqrt(2.0 * dl - 3.0) * sqrt(dl + dm) * sqrt(dl - dm));
+    }
+  }
+  const double scalef = 1.0e-280;
+  std::vector<double> pmm(Mpad, 0.0), sq(Mpad, 0.0);
+  pmm[0] = 1.0;   // zonal column is unscaled
+  {
+    double v = sqrt(2.0) * scalef;
+    for (int m = 1; m <= mmax; ++m) {
+      v = v * sqrt(2.0 * m + 1.0) / sqrt(2.0 * m);
+      pmm[m] = v;
+    }
+    for (int m = 0; m <= mmax; ++m) sq[m] = sqrt(2.0 * m + 3.0);
+  }
+  // rescale[h][m] = u^m / scalef by sequential products, u = sqrt(1-x^2) with 0 -> eps
+  std::vector<double> rescale((size_t)nlat * Mpad, 0.0), xs(costh, costh + nlat), ws(int_fact, int_fact + nlat);
+  for (int h = 0; h < nlat; ++h) {
+    double u = sqrt(1.0 - costh[h] * costh[h]);
+    if (u == 0.0) u = 2.220446049250313e-16;
+    double r = 1.0 / scalef;
+    rescale[(size_t)h * Mpad] = 1.0;
+    for (int m = 1; m <= mmax; ++m) {
+      r = r * u;
+      rescale[(size_t)h * Mpad + m] = r;
+    }
+  }
+  if ((rc = upload(&pl->trig, trig)) || (rc = upload(&pl->f1, f1)) || (rc = upload(&pl->f2, f2)) ||
+      (rc = upload(&pl->pmm, pmm)) || (rc = upload(&pl->sq, sq)) || (rc = upload(&pl->rescale, rescale)) ||
+      (rc = upload(&pl->x, xs)) || (rc = upload(&pl->w, ws)) ||
+      (rc = upload(&pl->lb_first_tile_dev, pl->lb_first_tile))) {
+    delete pl;
+    return rc;
+  }
+  *out = pl;
+  return MHB200_OK;
+}
+
+int mhb200_plan_destroy(mhb200_plan* pl) {
+  if (!pl) return MHB200_OK;
+  cudaSetDevice(pl->device);
+  cudaFree(pl->trig);
+  cudaFree(pl->f1);
+  cudaFree(pl->f2);
+  cudaFree(pl->pmm);
+  cudaFree(pl->sq);
+  cudaFree(pl->rescale);
+  cudaFree(pl->x);
+  cudaFree(pl->w);
+  cudaFree(pl->lb_first_tile_dev);
+  if (pl->stage_dev) cudaFree(pl->stage_dev);
+  if (pl->sched.segs_dev) cudaFree(pl->sched.segs_dev);
+  if (pl->sched.cta_seg_begin_dev) cudaFree(pl->sched.cta_seg_begin_dev);
+  if (pl->sched.tile_slot_begin_dev) cudaFree(pl->sched.tile_slot_begin_dev);
+  delete pl;
+  return MHB200_OK;
+}
+
+size_t mhb200_grid_workspace_bytes(const mhb200_plan* pl, int nbatch, int nlev) {
+  (void)nlev;
+  if (!pl || nbatch < 1) return 0;
+  return max_segments(pl, nbatch) * SLOT_DOUBLES * sizeof(double);
+}
+
+int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const int64_t Ps[3], const double* G,
+                               const int64_t Gs[3], const double* R, const int64_t Rs[3], int nbatch,
+                               double rad_e, const double* dfactor, const double* plm_table, double* clm_out,
+                               double* slm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  mhb200_plan* pl = const_cast<mhb200_plan*>(cpl);
+  if (!pl || !P || !G || !R || !Ps || !Gs || !Rs || nbatch < 1 || !dfactor || !clm_out || !slm_out || !workspace) {
+    set_err("mhb200_pressure_stokes_f64: bad argument");
+    return MHB200_EINVAL;
+  }
+  if (workspace_bytes < mhb200_grid_workspace_bytes(pl, nbatch, 0)) {
+    set_err("mhb200_pressure_stokes_f64: workspace too small");
+    return MHB200_EWORKSPACE;
+  }
+  std::lock_guard<std::mutex> lock(pl->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  MHB_CUDA(cudaSetDevice(pl->device));
+  int rc;
+  if ((rc = build_schedule(pl, nbatch, 0, MODE_PRESSURE)) != MHB200_OK) return rc;
+  pl->stage_reserved = 0;
+  GridParams gp;
+  fill_plan_params(pl, gp);
+  gp.plm_table = plm_table;
+  gp.slots = (double*)workspace;
+  gp.P = P;
+  gp.G = G;
+  gp.R = R;
+  for (int i = 0; i < 3; ++i) {
+    gp.Ps[i] = Ps[i];
+    gp.Gs[i] = Gs[i];
+    gp.Rs[i] = Rs[i];
+  }
+  gp.rad_e = rad_e;
+  if ((rc = launch_ring<MODE_PRESSURE, double>(gp, pl->sched.ncta, st)) != MHB200_OK) return rc;
+  return finish_reduce(pl, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+}
+
+int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH, const void* dP,
+                             int64_t batch_stride, const double* field_scale, const double* geoid,
+                             const int64_t geoid_stride[2], const double* ring_tab, const double* lon_tab,
+                             int nlev, int nbatch, int method, double rad_e, const double* dfactor,
+                             const double* plm_table, double* clm_out, double* slm_out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  mhb200_plan* pl = const_cast<mhb200_plan*>(cpl);
+  if (!pl || !GPH || !dP || !ring_tab || !lon_tab || nlev < 1 || nbatch < 1 || !dfactor || !clm_out ||
+      !slm_out || !workspace || (dtype != MHB200_F64 && dtype != MHB200_F32) ||
+      (method != MHB200_METHOD_BC05 && method != MHB200_METHOD_SW02) || (geoid && !geoid_stride)) {
+    set_err("mhb200_atmosphere_stokes: bad argument");
+    return MHB200_EINVAL;
+  }
+  if (workspace_bytes < mhb200_grid_workspace_bytes(pl, nbatch, nlev)) {
+    set_err("mhb200_atmosphere_stokes: workspace too small");
+    return MHB200_EWORKSPACE;
+  }
+  std::lock_guard<std::mutex> lock(pl->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  MHB_CUDA(cudaSetDevice(pl->device));
+  const int mode = (method == MHB200_METHOD_BC05) ? MODE_ATM_BC05 : MODE_ATM_SW02;
+  int rc;
+  if ((rc = build_schedule(pl, nbatch, nlev, mode)) != MHB200_OK) return rc;
+  const size_t nl = (size_t)pl->lmax + 1;
+  pl->stage_reserved = field_scale ? 2 * (size_t)nbatch : 0;
+  if ((rc = ensure_stage(pl, nl + 2 * (size_t)nbatch)) != MHB200_OK) return rc;
+  if (field_scale && (rc = stage(pl, field_scale, 2 * (size_t)nbatch, 0, st)) != MHB200_OK) return rc;
+  GridParams gp;
+  fill_plan_params(pl, gp);
+  gp.plm_table = plm_table;
+  gp.slots = (double*)workspace;
+  gp.GPH = GPH;
+  gp.dP = dP;
+  gp.batch_stride = batch_stride;
+  gp.field_scale = field_scale ? pl->stage_dev : nullptr;
+  gp.geoid = geoid;
+  gp.geo_s0 = geoid ? geoid_stride[0] : 0;
+  gp.geo_s1 = geoid ? geoid_stride[1] : 0;
+  gp.ring_tab = ring_tab;
+  gp.lon_tab = lon_tab;
+  gp.nlev = nlev;
+  gp.rad_e = rad_e;
+  const int ncta = pl->sched.ncta;
+  if (mode == MODE_ATM_BC05)
+    rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_BC05, double>(gp, ncta, st)
+                               : launch_ring<MODE_ATM_BC05, float>(gp, ncta, st);
+  else
+    rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_SW02, double>(gp, ncta, st)
+                               : launch_ring<MODE_ATM_SW02, float>(gp, ncta, st);
+  if (rc != MHB200_OK) return rc;
+  return finish_reduce(pl, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+"""
+Parity tests proper (GPU): the CUDA path, called through the Python drop-in operators and the
+C ABI, against (a) the committed golden fixtures produced by the unmodified reference files and
+(b) the NumPy oracle run on the same seeded inputs.  Gate: max|delta| / max|ref| <= 1e-12 over
+clm and slm jointly; structural properties exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases
+from parity import TOL, rel_to_max, assert_structure
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _ops():
+    import model_harmonics_b200 as mh
+    return mh
+
+
+@pytest.mark.parametrize('name', sorted(golden_cases.CASES))
+def test_cuda_matches_golden_and_oracle(name):
+    from oracle import stokes_oracle
+    mh = _ops()
+    func, args, kwargs = golden_cases.build(name)
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    Y = getattr(mh, func)(*args, **kwargs)
+    lmax, mmax = int(gold['lmax']), int(gold['mmax'])
+    assert int(Y.lmax) == lmax and int(Y.mmax) == mmax
+    assert_structure(Y.clm, Y.slm, lmax, mmax)
+    e_gold = rel_to_max(Y.clm, Y.slm, gold['clm'], gold['slm'])
+    O = getattr(stokes_oracle, func)(*args, **kwargs)
+    e_orc = rel_to_max(Y.clm, Y.slm, O.clm, O.slm)
+    print('%s: vs golden %.2e, vs oracle %.2e' % (name, e_gold, e_orc))
+    assert e_gold <= TOL, 'vs golden: %.3e' % e_gold
+    assert e_orc <= TOL, 'vs oracle: %.3e' % e_orc
+
+
+def test_inputs_not_modified_and_rerun_bitwise():
+    mh = _ops()
+    func, args, kwargs = golden_cases.build('atmosphere_bc05')
+    before = [np.copy(a) for a in args]
+    A = mh.gen_atmosphere_stokes(*args, **kwargs)
+    B = mh.gen_atmosphere_stokes(*args, **kwargs)
+    for a, b in zip(args, before):
+        assert np.array_equal(a, b)
+    # fixed-order reductions: run-to-run bit reproducible
+    assert np.array_equal(A.clm, B.clm) and np.array_equal(A.slm, B.slm)
+
+
+def test_plm_argument_paths(monkeypatch):
+    """PLM given: standard table -> recomputed on the fly; foreign table -> used as given."""
+    from oracle import stokes_oracle
+    from oracle.gravtk_standin import plm_holmes
+    mh = _ops()
+    func, args, kwargs = golden_cases.build('pressure_options')
+    lat = args[4]
+    L = kwargs['LMAX']
+    PLM, _ = plm_holmes(L, np.cos(np.radians(90.0 - lat)))
+    base = mh.gen_pressure_stokes(*args, **kwargs)
+    with_tab = mh.gen_pressure_stokes(*args, PLM=PLM, **kwargs)
+    assert rel_to_max(with_tab.clm, with_tab.slm, base.clm, base.slm) <= 1e-14
+    monkeypatch.setenv('MHB200_PLM_MODE', 'table')
+    forced = mh.gen_pressure_stokes(*args, PLM=PLM.copy(), **kwargs)
+    assert rel_to_max(forced.clm, forced.slm, base.clm, base.slm) <= TOL
+    monkeypatch.delenv('MHB200_PLM_MODE')
+    # a table from different colatitudes (e.g. geocentric) must be honoured
+    PLM2, _ = plm_holmes(L, np.cos(np.radians(90.0 - 0.995 * lat)))
+    got = mh.gen_pressure_stokes(*args, PLM=PLM2, **kwargs)
+    want = stokes_oracle.gen_pressure_stokes(*args, PLM=PLM2, **kwargs)
+    assert rel_to_max(got.clm, got.slm, want.clm, want.slm) <= TOL
+
+
+def test_float32_cubes_match_float64_of_same_values():
+    mh = _ops()
+    func, args, kwargs = golden_cases.build('atmosphere_levels37')
+    GPH32, dP32 = args[0].astype(np.float32), args[1].astype(np.float32)
+    A = mh.gen_atmosphere_stokes(GPH32, dP32, *args[2:], **kwargs)
+    B = mh.gen_atmosphere_stokes(GPH32.astype(np.float64), dP32.astype(np.float64), *args[2:], **kwargs)
+    assert np.array_equal(A.clm, B.clm) and np.array_equal(A.slm, B.slm)
+
+
+def test_batch_entry_points_match_single_calls():
+    import torch
+    from model_harmonics_b200 import testing as syn
+    mh = _ops()
+    # pressure: static geometry, 5 fields
+    lon, lat = syn.grid_axes(46, 90)
+    G, R = syn.surface_geometry(lon, lat, seed=3)
+    P = syn.pressure_fields(46, 90, 5, seed=10)
+    LOVE = syn.love_numbers(30)
+    clm, slm = mh.pressure_stokes_batch(P, G, R, lon, lat, LMAX=30, LOVE=LOVE)
+    for t in range(5):
+        Y = mh.gen_pressure_stokes(P[t], G, R, lon, lat, LMAX=30, LOVE=LOVE)
+        assert np.array_equal(Y.clm, clm[t]) and np.array_equal(Y.slm, slm[t])
+    # atmosphere: shared cube + per-field scale factors == explicit scaled cubes
+    GPH, dP, geoid = syn.atmosphere_cube(6, 46, 90, seed=5)
+    scales = np.array([syn.atmosphere_field_scalars(t) for t in (0, 7, 123)])
+    kw = dict(LMAX=30, ELLIPSOID='WGS84', GEOID=geoid, LOVE=LOVE)
+    clm, slm = mh.atmosphere_stokes_batch(GPH, dP, lon, lat, field_scale=scales, **kw)
+    for i in range(3):
+        Y = mh.gen_atmosphere_stokes(GPH * scales[i, 0], dP * scales[i, 1], lon, lat, **kw)
+        assert np.array_equal(Y.clm, clm[i]) and np.array_equal(Y.slm, slm[i])
+    # device-resident inputs are used in place
+    Pd = torch.from_numpy(P).cuda()
+    c2, s2 = mh.pressure_stokes_batch(Pd, torch.from_numpy(G).cuda(), torch.from_numpy(R).cuda(), lon, lat,
+                                      LMAX=30, LOVE=LOVE, as_numpy=False)
+    assert c2.is_cuda and np.array_equal(c2.cpu().numpy(), mh.pressure_stokes_batch(P, G, R, lon, lat, LMAX=30, LOVE=LOVE)[0])
+
+
+def test_error_conventions():
+    mh = _ops()
+    func, args, kwargs = golden_cases.build('atmosphere_weight')
+    bad = dict(kwargs)
+    bad['METHOD'] = 'XX'
+    with pytest.raises(ValueError):
+        mh.gen_atmosphere_stokes(*args, **bad)
+    bad = dict(kwargs)
+    bad['ELLIPSOID'] = None
+    with pytest.raises(AttributeError):
+        mh.gen_atmosphere_stokes(*args, **bad)
+    bad = dict(kwargs)
+    bad['ELLIPSOID'] = 'NOPE'
+    with pytest.raises(AssertionError):
+        mh.gen_atmosphere_stokes(*args, **bad)
+    bad = dict(kwargs)
+    bad['GEOID'] = None
+    with pytest.raises(TypeError):
+        mh.gen_atmosphere_stokes(*args, **bad)
+    bad = dict(kwargs)
+    bad['LOVE'] = None
+    with pytest.raises(TypeError):
+        mh.gen_atmosphere_stokes(*args, **bad)
+    func, args, kwargs = golden_cases.build('points_mmax0')
+    bad = dict(kwargs)
+    bad['AREA'] = None
+    with pytest.raises(AttributeError):
+        mh.gen_point_pressure(*args, **bad)
