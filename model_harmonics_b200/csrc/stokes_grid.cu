@@ -43,7 +43,12 @@ constexpr int PLM_PITCH = 65;
 constexpr int CS_ROWS = 36;       // per-thread accumulators kept in shared memory
 constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
 constexpr int DF_MAX = 448;
-constexpr size_t SMEM_BYTES = (size_t)(KS_MAX * 256 + CS_ROWS * NT + MBLK * PLM_PITCH) * sizeof(double);
+constexpr int LEV_GROUP = 40;      // levels staged per geometry pass
+// region 0 holds the B chunk (64 KB) and, before it is written, the staged (u0, r) pairs of the
+// atmosphere geometry pass (LEV_GROUP x 128 x 16 B = 80 KB)
+constexpr int REGION0_DOUBLES = LEV_GROUP * KC_MAX * 2;
+static_assert(REGION0_DOUBLES >= KS_MAX * 256, "region 0 must hold the B chunk");
+constexpr size_t SMEM_BYTES = (size_t)(REGION0_DOUBLES + CS_ROWS * NT + MBLK * PLM_PITCH) * sizeof(double);
 
 enum Mode { MODE_PRESSURE = 0, MODE_ATM_BC05 = 1, MODE_ATM_SW02 = 2 };
 
@@ -125,13 +130,25 @@ __device__ __forceinline__ void legendre_ring(const GridParams& p, int h, int lb
   if (m + 1 >= lbase) row[m + 1 - lbase] = __dmul_rn(__dmul_rn(p1, rs), wh);
   const double* f1 = p.f1 + m;
   const double* f2 = p.f2 + m;
-  for (int l = m + 2; l <= lend; ++l) {
-    const double a = __ldg(f1 + (size_t)l * p.Mpad);
-    const double b = __ldg(f2 + (size_t)l * p.Mpad);
-    const double pl = __dsub_rn(__dmul_rn(__dmul_rn(x, a), p1), __dmul_rn(b, p2));
-    p2 = p1;
-    p1 = pl;
-    if (l >= lbase) row[l - lbase] = __dmul_rn(__dmul_rn(pl, rs), wh);
+  for (int l0 = m + 2; l0 <= lend; l0 += 8) {
+    // multipliers for 8 degrees are fetched together so their L2 latency overlaps
+    double a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = min(l0 + i, lend);
+      a[i] = __ldg(f1 + (size_t)l * p.Mpad);
+      b[i] = __ldg(f2 + (size_t)l * p.Mpad);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = l0 + i;
+      if (l <= lend) {
+        const double pl = __dsub_rn(__dmul_rn(__dmul_rn(x, a[i]), p1), __dmul_rn(b[i], p2));
+        p2 = p1;
+        p1 = pl;
+        if (l >= lbase) row[l - lbase] = __dmul_rn(__dmul_rn(pl, rs), wh);
+      }
+    }
   }
 }
 
@@ -171,26 +188,88 @@ __device__ __forceinline__ void produce_pressure(const GridParams& p, int t, int
   }
 }
 
+// Branch-free fp64 reciprocal and square root (Newton from the fp32 SFU seed).  The library
+// sqrt()/division carry special-case branches that split the basic block and serialise the
+// geometry chain; operands here are always normal and far from the range limits.
+__device__ __forceinline__ double fast_rcp(double a) {
+  double y = (double)__frcp_rn((float)a);
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_div(double n, double d) {
+  const double y = fast_rcp(d);
+  const double q = n * y;
+  return fma(fma(-d, q, n), y, q);      // one correction step: within 1 ulp
+}
+__device__ __forceinline__ double fast_sqrt(double a) {
+  const double y = (double)rsqrtf((float)a);
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  return fma(fma(-g, g, a), h, g);
+}
+
 // One level's contribution to the 32 degrees this thread owns:  acc[j] += u * r^j.
-// Stride-8 scheme: 7 powers + per stride one add, seven FMAs and one multiply
-// (1.25 fp64-pipe slots per degree instead of 2 for "acc += t; t *= r").
+// Stride-8 scheme: 7 powers + per stride one add and seven FMAs
+// (~1.25 fp64-pipe slots per degree instead of 2 for "acc += t; t *= r").
 __device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, double r, int half) {
   const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
   const double r5 = r4 * r, r6 = r4 * r2, r7 = r4 * r3, r8 = r4 * r4;
   const double r16 = r8 * r8, r32 = r16 * r16;
-  u *= (half ? r32 : 1.0);
+  double us[4];
+  us[0] = u * (half ? r32 : 1.0);
+  us[1] = us[0] * r8;
+  us[2] = us[0] * r16;
+  us[3] = us[1] * r16;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    acc[8 * s + 0] += u;
-    acc[8 * s + 1] = fma(u, r, acc[8 * s + 1]);
-    acc[8 * s + 2] = fma(u, r2, acc[8 * s + 2]);
-    acc[8 * s + 3] = fma(u, r3, acc[8 * s + 3]);
-    acc[8 * s + 4] = fma(u, r4, acc[8 * s + 4]);
-    acc[8 * s + 5] = fma(u, r5, acc[8 * s + 5]);
-    acc[8 * s + 6] = fma(u, r6, acc[8 * s + 6]);
-    acc[8 * s + 7] = fma(u, r7, acc[8 * s + 7]);
-    u *= r8;
+    const double v = us[s];
+    acc[8 * s + 0] += v;
+    acc[8 * s + 1] = fma(v, r, acc[8 * s + 1]);
+    acc[8 * s + 2] = fma(v, r2, acc[8 * s + 2]);
+    acc[8 * s + 3] = fma(v, r3, acc[8 * s + 3]);
+    acc[8 * s + 4] = fma(v, r4, acc[8 * s + 4]);
+    acc[8 * s + 5] = fma(v, r5, acc[8 * s + 5]);
+    acc[8 * s + 6] = fma(v, r6, acc[8 * s + 6]);
+    acc[8 * s + 7] = fma(v, r7, acc[8 * s + 7]);
   }
+}
+
+// per-column constants of the atmosphere geometry
+struct ColumnGeom {
+  double NG, NG1, cphi, sphi, geo_over;
+};
+
+// (u0, r) of one (level, column) element: u0 = -(dp/gamma) r^2 (BC05) or -(dp/g0) r^4 (SW02)
+template <int MODE>
+__device__ __forceinline__ double2 level_element(double z, double dpv, const ColumnGeom& c, double a1, double a2,
+                                                 double st, double ct, double gs, double c1, double rad_e,
+                                                 double inv_rad) {
+  double u0, r;
+  if (MODE == MODE_ATM_BC05) {
+    const double H = a1 * z + a2 * (z * z);                 // orthometric height (List 1958), :222-224
+    const double A = c.NG + H, B = c.NG1 + H;
+    const double As = A * st;
+    const double X = As * c.cphi, Y = As * c.sphi, Z = B * ct;
+    const double R = fast_sqrt(fma(Z, Z, fma(Y, Y, X * X))); // :226-230
+    r = R * inv_rad;
+    const double hr = H * inv_rad;
+    const double gam = gs * fma(3.0 * hr, hr, fma(-c1, hr, 1.0));   // :232-238
+    const double q = fast_div(dpv, gam);
+    u0 = -(q * r) * r;
+  } else {
+    r = fast_div(rad_e, rad_e - z) + c.geo_over;            // :258-260
+    const double q = fast_div(dpv, 9.80665);
+    const double r2 = r * r;
+    u0 = -(q * r2) * r2;
+  }
+  return make_double2(u0, r);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -198,97 +277,109 @@ __device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, do
 //   B[p,l] = - sum_k (dp_k/gamma_k) (R_k/rad_e)^(l+2)                      BC05
 //   B[p,l] = - sum_k (dp_k/g0) (rad_e/(rad_e-GPH_k) + GEOID/rad_e)^(l+4)   SW02
 // (the minus sign is the reference's einsum(m_phi, -pfactor), :270).
-// Lane pair (lane, lane^16) shares a column; the pair splits the levels for the geometry
-// (even/odd level) and the degrees for the accumulation (lower/upper 32).
+// Two passes per group of LEV_GROUP levels:
+//   geometry pass   : elementwise over (level, column), coalesced along lon, 4 independent
+//                     elements in flight per thread; (u0, r) staged in shared memory
+//   accumulate pass : lane pair (lane, lane^16) shares a column and splits the 64 degrees;
+//                     32 running sums per thread in registers
 // ---------------------------------------------------------------------------------------
 template <int MODE, typename Tin>
 __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, int h, int lb, int chunk,
                                                    double* Bs) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = warp * 16 + (lane & 15), half = lane >> 4;
-  const int pcol = chunk * p.kc + col;
-  const bool active = (col < p.kc) && (pcol < p.nlon);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double2* stg = reinterpret_cast<double2*>(Bs);            // [level in group][128 columns]
   const size_t lev_stride = (size_t)p.nlat * p.nlon;
-  const int pc = active ? pcol : 0;
-  const Tin* zp = (const Tin*)p.GPH + (size_t)t * p.batch_stride + (size_t)h * p.nlon + pc;
-  const Tin* dp = (const Tin*)p.dP + (size_t)t * p.batch_stride + (size_t)h * p.nlon + pc;
+  const int nlev = p.nlev;
+  const double inv_rad = 1.0 / p.rad_e;
   double sg = 1.0, sp = 1.0;
   if (p.field_scale != nullptr) {
     sg = p.field_scale[2 * t];
     sp = p.field_scale[2 * t + 1];
   }
-  const double geo = (p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + pc * p.geo_s1) : 0.0;
-  const double inv_rad = 1.0 / p.rad_e;
-  // ring (colatitude-only) and longitude-only factors, built on the host
+  // ring (colatitude-only) factors, built on the host
   const double a1 = p.ring_tab[0 * p.nlat + h], a2 = p.ring_tab[1 * p.nlat + h];
-  const double NG = p.ring_tab[2 * p.nlat + h] + geo;     // (N + GEOID)
-  const double NG1 = p.ring_tab[3 * p.nlat + h] + geo;    // (N(1-e^2) + GEOID)
   const double st = p.ring_tab[4 * p.nlat + h], ct = p.ring_tab[5 * p.nlat + h];
   const double gs = p.ring_tab[6 * p.nlat + h], c1 = p.ring_tab[7 * p.nlat + h];
-  const double cphi = p.lon_tab[pc], sphi = p.lon_tab[p.nlon + pc];
-  const double geo_over = geo / p.rad_e;
-  const double g0 = 9.80665;
 
+  // geometry-pass ownership: a fixed column, levels of parity tid>>7
+  const int gcol = tid & (KC_MAX - 1), gpar = tid >> 7;
+  const int gpcol = chunk * p.kc + gcol;
+  const bool gactive = (gcol < p.kc) && (gpcol < p.nlon);
+  const int gpc = gactive ? gpcol : 0;
+  ColumnGeom cg;
+  {
+    const double geo = (p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + gpc * p.geo_s1) : 0.0;
+    cg.NG = p.ring_tab[2 * p.nlat + h] + geo;     // (N + GEOID)
+    cg.NG1 = p.ring_tab[3 * p.nlat + h] + geo;    // (N(1-e^2) + GEOID)
+    cg.cphi = p.lon_tab[gpc];
+    cg.sphi = p.lon_tab[p.nlon + gpc];
+    cg.geo_over = geo / p.rad_e;
+  }
+  const Tin* zp = (const Tin*)p.GPH + (size_t)t * p.batch_stride + (size_t)h * p.nlon + gpc;
+  const Tin* dp = (const Tin*)p.dP + (size_t)t * p.batch_stride + (size_t)h * p.nlon + gpc;
+
+  // accumulate-pass ownership
+  const int acol = warp * 16 + (lane & 15), half = lane >> 4;
   double acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.0;
 
-  // software-pipelined level loop: the pair handles levels (k0, k0+1) per iteration
-  const int nlev = p.nlev;
-  double z_n = 0.0, d_n = 0.0;
-  {
-    const int k = half;
-    if (active && k < nlev) {
-      z_n = ld_as_double(zp + k * lev_stride);
-      d_n = ld_as_double(dp + k * lev_stride);
-    }
-  }
-  for (int k0 = 0; k0 < nlev; k0 += 2) {
-    const double z = sg * z_n, dpv = sp * d_n;
-    const bool valid = active && (k0 + half < nlev);
-    {
-      const int k = k0 + 2 + half;
-      z_n = 0.0;
-      d_n = 0.0;
-      if (active && k < nlev) {
-        z_n = ld_as_double(zp + k * lev_stride);
-        d_n = ld_as_double(dp + k * lev_stride);
+  for (int kg = 0; kg < nlev; kg += LEV_GROUP) {
+    const int ng = min(LEV_GROUP, nlev - kg);
+    // ---- geometry pass
+    for (int kk0 = gpar; kk0 < ng; kk0 += 8) {
+      double z[4], d[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = kk0 + 2 * i;
+        z[i] = 0.0;
+        d[i] = 0.0;
+        if (gactive && kk < ng) {
+          z[i] = ld_as_double(zp + (size_t)(kg + kk) * lev_stride);
+          d[i] = ld_as_double(dp + (size_t)(kg + kk) * lev_stride);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = kk0 + 2 * i;
+        double2 e = level_element<MODE>(sg * z[i], sp * d[i], cg, a1, a2, st, ct, gs, c1, p.rad_e, inv_rad);
+        if (lb > 0) e.x *= ipow(e.y, lb * LBLK);
+        if (!gactive) e = make_double2(0.0, 1.0);
+        if (kk < ng) stg[kk * KC_MAX + gcol] = e;
       }
     }
-    double u0, r;
-    if (MODE == MODE_ATM_BC05) {
-      // orthometric height (List 1958), :222-224
-      const double H = a1 * z + a2 * (z * z);
-      const double A = NG + H, B = NG1 + H;
-      const double As = A * st;
-      const double X = As * cphi, Y = As * sphi, Z = B * ct;
-      const double R = sqrt(fma(Z, Z, fma(Y, Y, X * X)));      // :226-230
-      r = R * inv_rad;
-      const double hr = H * inv_rad;
-      const double gam = gs * fma(3.0 * hr, hr, fma(-c1, hr, 1.0));   // :232-238
-      const double q = dpv / gam;
-      u0 = -(q * r) * r;
-    } else {
-      r = p.rad_e / (p.rad_e - z) + geo_over;                  // :258-260
-      const double q = dpv / g0;
-      const double r2 = r * r;
-      u0 = -(q * r2) * r2;
+    __syncthreads();
+    // ---- accumulate pass
+#pragma unroll 2
+    for (int kk = 0; kk < ng; ++kk) {
+      const double2 e = stg[kk * KC_MAX + acol];
+      accumulate_level(acc, e.x, e.y, half);
     }
-    if (lb > 0) u0 *= ipow(r, lb * LBLK);
-    if (!valid) {
-      u0 = 0.0;
-      r = 1.0;
-    }
-    const double pu = __shfl_xor_sync(0xffffffffu, u0, 16);
-    const double pr = __shfl_xor_sync(0xffffffffu, r, 16);
-    // even level first, then odd, for both halves (fixed summation order)
-    accumulate_level(acc, half ? pu : u0, half ? pr : r, half);
-    accumulate_level(acc, half ? u0 : pu, half ? r : pr, half);
+    __syncthreads();      // staging is overwritten by the next group / by the B chunk
   }
-  if (col < p.kc) {
+  if (acol < p.kc) {
     const int l0 = 32 * half;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) Bs[bs_index(l0 + j, col)] = acc[j];
+    for (int j = 0; j < 32; ++j) Bs[bs_index(l0 + j, acol)] = acc[j];
+  }
+}
+
+// L2 prefetch of the cube data the next chunk's geometry pass will read (issued before the
+// contraction phase so that DRAM latency is off the critical path)
+template <typename Tin>
+__device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
+  if (h >= p.nlat) return;
+  const size_t lev_stride = (size_t)p.nlat * p.nlon;
+  const int per_line = 128 / (int)sizeof(Tin);
+  const int lines = (p.kc + per_line - 1) / per_line + 1;
+  const size_t base = (size_t)t * p.batch_stride + (size_t)h * p.nlon + (size_t)chunk * p.kc;
+  for (int i = threadIdx.x; i < p.nlev * lines * 2; i += NT) {
+    const int arr = i & 1, j = i >> 1;
+    const int k = j / lines, ln = j % lines;
+    const int col = min(ln * per_line, p.kc - 1);
+    if ((size_t)chunk * p.kc + col >= (size_t)p.nlon) continue;
+    const Tin* q = (const Tin*)(arr ? p.dP : p.GPH) + base + (size_t)k * lev_stride + col;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
   }
 }
 
@@ -331,39 +422,47 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
         produce_atmosphere<MODE, Tin>(p, seg.t, h, seg.lb, chunk, Bs);
       __syncthreads();
 
-      // contraction over the chunk's longitudes; trig fragments straight from L2 (fragment-major
-      // table: one coalesced 256-byte load per fragment), B fragments from shared memory
-      const double* Ablk = p.trig + ((size_t)(seg.mb * p.nks_total + chunk * nksc) * 16) * 32 + lane;
-      int ks = kpar;
-      double aAc = 0, aAs = 0, aBc = 0, aBs = 0;
-      if (ks < nksc) {
-        const double* a = Ablk + (size_t)ks * 512;
-        aAc = __ldg(a + (gA * 2) * 32);
-        aAs = __ldg(a + (gA * 2 + 1) * 32);
-        if (DIAG) {
-          aBc = __ldg(a + (gB * 2) * 32);
-          aBs = __ldg(a + (gB * 2 + 1) * 32);
-        }
+      if (MODE != MODE_PRESSURE) {
+        // start pulling the next chunk's (or next ring's first chunk's) cube data into L2
+        const bool last = (chunk + 1 == p.nchunks);
+        prefetch_chunk<Tin>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }
-      for (; ks < nksc; ks += kstep) {
-        const double cAc = aAc, cAs = aAs, cBc = aBc, cBs = aBs;
-        const int kn = ks + kstep;
-        if (kn < nksc) {
-          const double* a = Ablk + (size_t)kn * 512;
-          aAc = __ldg(a + (gA * 2) * 32);
-          aAs = __ldg(a + (gA * 2 + 1) * 32);
+      // contraction over the chunk's longitudes; trig fragments straight from L2 (fragment-major
+      // table: one coalesced 256-byte load per fragment, prefetched two k-steps ahead),
+      // B fragments from shared memory
+      const double* Ablk = p.trig + ((size_t)(seg.mb * p.nks_total + chunk * nksc) * 16) * 32 + lane;
+      constexpr int NA = DIAG ? 4 : 2;
+      double a0[NA], a1[NA];
+      auto load_a = [&](double(&a)[NA], int k) {
+        if (k < nksc) {
+          const double* ap = Ablk + (size_t)k * 512;
+          a[0] = __ldg(ap + (gA * 2) * 32);
+          a[1] = __ldg(ap + (gA * 2 + 1) * 32);
           if (DIAG) {
-            aBc = __ldg(a + (gB * 2) * 32);
-            aBs = __ldg(a + (gB * 2 + 1) * 32);
+            a[2] = __ldg(ap + (gB * 2) * 32);
+            a[3] = __ldg(ap + (gB * 2 + 1) * 32);
           }
         }
+      };
+      load_a(a0, kpar);
+      load_a(a1, kpar + kstep);
+      for (int ks = kpar; ks < nksc; ks += kstep) {
+        double c[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          c[i] = a0[i];
+          a0[i] = a1[i];
+        }
+        load_a(a1, ks + 2 * kstep);
         const double* Bk = Bs + ks * 256 + ((((lane >> 2) + ks) & 7) << 2) + (lane & 3);
+        double b[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          const double b = Bk[lt[j] * 32];
           const bool first = (!DIAG) || (j < nA);
-          dmma884(acc[j][0][0], acc[j][0][1], first ? cAc : cBc, b);
-          dmma884(acc[j][1][0], acc[j][1][1], first ? cAs : cBs, b);
+          dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], b[j]);
+          dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], b[j]);
         }
       }
       __syncthreads();
@@ -414,7 +513,7 @@ template <int MODE, typename Tin>
 __global__ void __launch_bounds__(NT, 1) stokes_ring_kernel(const GridParams p) {
   extern __shared__ double smem[];
   double* Bs = smem;
-  double* Cs = Bs + KS_MAX * 256;
+  double* Cs = Bs + REGION0_DOUBLES;
   double* plm_s = Cs + CS_ROWS * NT;
   const int sb = p.cta_seg_begin[blockIdx.x], se = p.cta_seg_begin[blockIdx.x + 1];
   for (int s = sb; s < se; ++s) {

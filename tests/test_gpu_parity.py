@@ -96,7 +96,8 @@ def test_batch_entry_points_match_single_calls():
     clm, slm = mh.pressure_stokes_batch(P, G, R, lon, lat, LMAX=30, LOVE=LOVE)
     for t in range(5):
         Y = mh.gen_pressure_stokes(P[t], G, R, lon, lat, LMAX=30, LOVE=LOVE)
-        assert np.array_equal(Y.clm, clm[t]) and np.array_equal(Y.slm, slm[t])
+        # a different batch size is a different static schedule, i.e. a different (fixed) summation order
+        assert rel_to_max(clm[t], slm[t], Y.clm, Y.slm) <= 1e-14
     # atmosphere: shared cube + per-field scale factors == explicit scaled cubes
     GPH, dP, geoid = syn.atmosphere_cube(6, 46, 90, seed=5)
     scales = np.array([syn.atmosphere_field_scalars(t) for t in (0, 7, 123)])
@@ -104,7 +105,7 @@ def test_batch_entry_points_match_single_calls():
     clm, slm = mh.atmosphere_stokes_batch(GPH, dP, lon, lat, field_scale=scales, **kw)
     for i in range(3):
         Y = mh.gen_atmosphere_stokes(GPH * scales[i, 0], dP * scales[i, 1], lon, lat, **kw)
-        assert np.array_equal(Y.clm, clm[i]) and np.array_equal(Y.slm, slm[i])
+        assert rel_to_max(clm[i], slm[i], Y.clm, Y.slm) <= 1e-14
     # device-resident inputs are used in place
     Pd = torch.from_numpy(P).cuda()
     c2, s2 = mh.pressure_stokes_batch(Pd, torch.from_numpy(G).cuda(), torch.from_numpy(R).cuda(), lon, lat,
