@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 SRC=model_harmonics_b200/csrc
-OUT=model_harmonics_b200/libmhb200.so
+OUT=${MHB_OUT:-model_harmonics_b200/libmhb200.so}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 mkdir -p build
 pids=()

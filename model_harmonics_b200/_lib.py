@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmhb200.so')
+LIB_PATH = os.environ.get('MHB200_LIB', os.path.join(_HERE, 'libmhb200.so'))
 
 OK = 0
 METHOD_BC05, METHOD_SW02 = 0, 1

@@ -52,8 +52,9 @@ constexpr size_t SMEM_BYTES = (size_t)(REGION0_DOUBLES + CS_ROWS * NT + MBLK * P
 
 enum Mode { MODE_PRESSURE = 0, MODE_ATM_BC05 = 1, MODE_ATM_SW02 = 2 };
 
+// work unit = (ring, longitude chunk), linearised as u = ring * nchunks + chunk
 struct Segment {
-  int t, lb, mb, h0, h1, pad;
+  int t, lb, mb, u0, u1, pad;
 };
 
 struct GridParams {
@@ -326,9 +327,9 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 
   for (int kg = 0; kg < nlev; kg += LEV_GROUP) {
     const int ng = min(LEV_GROUP, nlev - kg);
-    // ---- geometry pass
-    for (int kk0 = gpar; kk0 < ng; kk0 += 8) {
-      double z[4], d[4];
+    // ---- geometry pass (loads of the next 4 elements are in flight while 4 are computed)
+    double zc[4], dc[4];
+    auto load4 = [&](double(&z)[4], double(&d)[4], int kk0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int kk = kk0 + 2 * i;
@@ -339,13 +340,23 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
           d[i] = ld_as_double(dp + (size_t)(kg + kk) * lev_stride);
         }
       }
+    };
+    load4(zc, dc, gpar);
+    for (int kk0 = gpar; kk0 < ng; kk0 += 8) {
+      double zn[4], dn[4];
+      load4(zn, dn, kk0 + 8);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int kk = kk0 + 2 * i;
-        double2 e = level_element<MODE>(sg * z[i], sp * d[i], cg, a1, a2, st, ct, gs, c1, p.rad_e, inv_rad);
+        double2 e = level_element<MODE>(sg * zc[i], sp * dc[i], cg, a1, a2, st, ct, gs, c1, p.rad_e, inv_rad);
         if (lb > 0) e.x *= ipow(e.y, lb * LBLK);
         if (!gactive) e = make_double2(0.0, 1.0);
         if (kk < ng) stg[kk * KC_MAX + gcol] = e;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        zc[i] = zn[i];
+        dc[i] = dn[i];
       }
     }
     __syncthreads();
@@ -384,38 +395,63 @@ __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h
 }
 
 // ---------------------------------------------------------------------------------------
-// One segment: rings h0..h1 of tile (lb, mb) of field t.
-// DIAG tile (lb == mb): only 8x8 sub-tiles with degree-tile >= order-tile are needed (36 of
-// 64).  Warp w: order groups gA = w&3 and gB = 7-gA (9 sub-tile pairs, balanced), k-steps of
-// parity w>>2.  FULL tile: warp w owns order group w, all 8 degree tiles, every k-step.
+// One segment: work units [u0, u1) (unit = ring * nchunks + chunk) of tile (lb, mb) of field t.
+//
+// DIAG tile (lb == mb): only the 8x8 sub-tiles with degree-tile >= order-tile are needed (36 of
+// 64).  The four warps {q, q+4} ... share the order groups gA = q and gB = 7-q, i.e. 9
+// (order-group, degree-tile) pairs j = 0..8.  Warp q owns pairs 0..3, warp q+4 owns pairs 5..8,
+// and the "swing" pair 4 is done by warp q on even k-steps and by warp q+4 on odd k-steps:
+// 9 DMMA pairs per two k-steps for every warp (perfectly balanced), 5 accumulator pairs per
+// thread.  FULL tile: warp w owns order group w and all 8 degree tiles.
 // ---------------------------------------------------------------------------------------
+#ifndef MHB_SWING
+#define MHB_SWING 0
+#endif
 template <int MODE, typename Tin, bool DIAG>
 __device__ __forceinline__ void run_segment(const GridParams& p, const Segment seg, int slot_index,
                                             double* Bs, double* Cs, double* plm_s) {
-  constexpr int NP = DIAG ? 9 : 8;
+  // SW = swing mapping (above); !SW = each warp of a quad does all 9 pairs on k-steps of one parity
+  constexpr bool SW = (MHB_SWING != 0);
+  constexpr int NP = DIAG ? (SW ? 5 : 9) : 8;          // accumulator pairs per thread
+  constexpr int KSTRIDE = (DIAG && !SW) ? 2 : 1;
+  constexpr int NA = DIAG ? 4 : 2;          // trig fragments per k-step
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = DIAG ? (warp >> 2) : 0;
   const int gA = DIAG ? (warp & 3) : warp;
   const int gB = DIAG ? (7 - gA) : warp;
   const int nA = DIAG ? (8 - gA) : 8;
-  const int kpar = DIAG ? (warp >> 2) : 0;
-  const int kstep = DIAG ? 2 : 1;
   const int nksc = p.kc >> 2;
 
-  int lt[NP];
+  int lt[NP];          // degree tile of local pair j
+  bool inA[NP];        // pair belongs to order group gA (else gB)
 #pragma unroll
-  for (int j = 0; j < NP; ++j) lt[j] = DIAG ? ((j < nA) ? (gA + j) : (j - 1)) : j;
+  for (int j = 0; j < NP; ++j) {
+    if (DIAG) {
+      const int jg = SW ? ((j < 4) ? (sub ? 5 + j : j) : 4) : j;     // index in the quad's list of 9 pairs
+      inA[j] = (jg < nA);
+      lt[j] = inA[j] ? (gA + jg) : (jg - 1);
+    } else {
+      inA[j] = true;
+      lt[j] = j;
+    }
+  }
 
 #pragma unroll
   for (int i = 0; i < NP * 4; ++i) Cs[i * NT + tid] = 0.0;
 
-  for (int h = seg.h0; h < seg.h1; ++h) {
+  const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
+  for (int h = hfirst; h <= hlast; ++h) {
+    // chunks of this ring that belong to the segment (partial rings are fine: the Legendre
+    // weighting below is linear in the longitude partial sums)
+    const int cbeg = (h == hfirst) ? (seg.u0 - h * p.nchunks) : 0;
+    const int cend = (h == hlast) ? (seg.u1 - h * p.nchunks) : p.nchunks;
     if (tid < MBLK) legendre_ring(p, h, seg.lb, seg.mb, tid, plm_s);
 
     double acc[NP][2][2];
 #pragma unroll
     for (int j = 0; j < NP; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
 
-    for (int chunk = 0; chunk < p.nchunks; ++chunk) {
+    for (int chunk = cbeg; chunk < cend; ++chunk) {
       if (MODE == MODE_PRESSURE)
         produce_pressure(p, seg.t, h, seg.lb, chunk, Bs);
       else
@@ -428,41 +464,48 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
         prefetch_chunk<Tin>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }
       // contraction over the chunk's longitudes; trig fragments straight from L2 (fragment-major
-      // table: one coalesced 256-byte load per fragment, prefetched two k-steps ahead),
-      // B fragments from shared memory
+      // table: one coalesced 256-byte load per fragment, prefetched three k-steps ahead in a
+      // register ring), B fragments from shared memory
       const double* Ablk = p.trig + ((size_t)(seg.mb * p.nks_total + chunk * nksc) * 16) * 32 + lane;
-      constexpr int NA = DIAG ? 4 : 2;
-      double a0[NA], a1[NA];
       auto load_a = [&](double(&a)[NA], int k) {
         if (k < nksc) {
           const double* ap = Ablk + (size_t)k * 512;
           a[0] = __ldg(ap + (gA * 2) * 32);
           a[1] = __ldg(ap + (gA * 2 + 1) * 32);
-          if (DIAG) {
+          if (DIAG && (sub || !SW)) {        // swing: only the second warp of a quad touches order group gB
             a[2] = __ldg(ap + (gB * 2) * 32);
             a[3] = __ldg(ap + (gB * 2 + 1) * 32);
           }
         }
       };
-      load_a(a0, kpar);
-      load_a(a1, kpar + kstep);
-      for (int ks = kpar; ks < nksc; ks += kstep) {
-        double c[NA];
+      double a[4][NA];
 #pragma unroll
-        for (int i = 0; i < NA; ++i) {
-          c[i] = a0[i];
-          a0[i] = a1[i];
-        }
-        load_a(a1, ks + 2 * kstep);
-        const double* Bk = Bs + ks * 256 + ((((lane >> 2) + ks) & 7) << 2) + (lane & 3);
-        double b[NP];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
+        for (int j = 0; j < NA; ++j) a[i][j] = 0.0;
+      const int k0 = (DIAG && !SW) ? sub : 0;
 #pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          const bool first = (!DIAG) || (j < nA);
-          dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], b[j]);
-          dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], b[j]);
+      for (int i = 0; i < 3; ++i) load_a(a[i], k0 + i * KSTRIDE);
+      // 4-deep ring, fully unrolled so no rotation copies shorten the prefetch distance;
+      // with stride 1 the k-step parity of ring slot u is u & 1 (compile time)
+      for (int ks = k0; ks < nksc; ks += 4 * KSTRIDE) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = ks + u * KSTRIDE;
+          if (k < nksc) {
+            load_a(a[(u + 3) & 3], k + 3 * KSTRIDE);
+            const double(&c)[NA] = a[u];
+            const double* Bk = Bs + k * 256 + ((((lane >> 2) + k) & 7) << 2) + (lane & 3);
+            double b[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              if (DIAG && SW && j == 4 && ((u & 1) != sub)) continue;     // swing pair: other warp's turn
+              dmma884(acc[j][0][0], acc[j][0][1], inA[j] ? c[0] : c[DIAG ? 2 : 0], b[j]);
+              dmma884(acc[j][1][0], acc[j][1][1], inA[j] ? c[1] : c[DIAG ? 3 : 1], b[j]);
+            }
+          }
         }
       }
       __syncthreads();
@@ -471,7 +514,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
     // ring epilogue: C += (w_h Plm) o Dring
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      const int g = ((!DIAG) || (j < nA)) ? gA : gB;
+      const int g = inA[j] ? gA : gB;
       const int m_local = g * 8 + (lane >> 2);
       const int l_local = lt[j] * 8 + 2 * (lane & 3);
       const double w0 = plm_s[m_local * PLM_PITCH + l_local];
@@ -488,21 +531,21 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
   // write the segment's partial sums: slot[cs][l_local][m_local]
   double* slot = p.slots + (size_t)slot_index * SLOT_DOUBLES;
-  if (!DIAG || tid < 128) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const int g = ((!DIAG) || (j < nA)) ? gA : gB;
-      const int m_local = g * 8 + (lane >> 2);
-      const int l_local = lt[j] * 8 + 2 * (lane & 3);
+  for (int j = 0; j < NP; ++j) {
+    if (DIAG && SW && j == 4 && sub) continue;        // the swing pair is written by the first warp
+    if (DIAG && !SW && sub) continue;             // parity mapping: first warp writes the sum of both
+    const int g = inA[j] ? gA : gB;
+    const int m_local = g * 8 + (lane >> 2);
+    const int l_local = lt[j] * 8 + 2 * (lane & 3);
 #pragma unroll
-      for (int cs = 0; cs < 2; ++cs) {
+    for (int cs = 0; cs < 2; ++cs) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int row = ((j * 2 + cs) * 2 + e) * NT;
-          double v = Cs[row + tid];
-          if (DIAG) v += Cs[row + tid + 128];   // the two k-parities
-          slot[(cs * LBLK + l_local + e) * MBLK + m_local] = v;
-        }
+      for (int e = 0; e < 2; ++e) {
+        const int row = ((j * 2 + cs) * 2 + e) * NT;
+        double v = Cs[row + tid];
+        if (DIAG && (j == 4 || !SW)) v += Cs[row + tid + 128];   // even + odd k-steps
+        slot[(cs * LBLK + l_local + e) * MBLK + m_local] = v;
       }
     }
   }
@@ -526,29 +569,39 @@ __global__ void __launch_bounds__(NT, 1) stokes_ring_kernel(const GridParams p) 
 }
 
 // Fixed-order reduction of the partial slots + degree factors (gen_pressure_stokes.py:205-206).
-// grid (lmax+1, nbatch), one thread per order.
-__global__ void stokes_reduce_kernel(const __grid_constant__ ReduceParams q) {
+// grid (lmax+1, nbatch), 256 threads: 4 interleaved partial sums per (l, m) -- independent
+// loads in flight -- combined in a fixed order, so results are bit-reproducible.
+__global__ void __launch_bounds__(256) stokes_reduce_kernel(const __grid_constant__ ReduceParams q) {
+  __shared__ double part[2][4][MBLK];
   const int l = blockIdx.x, t = blockIdx.y;
   const int ncol = q.mmax + 1;
   const double df = (q.dfactor_dev != nullptr) ? q.dfactor_dev[l] : q.dfactor[l];
   const int lb = l / LBLK, l_local = l % LBLK;
-  for (int m = threadIdx.x; m < ncol; m += blockDim.x) {
+  const int ml = threadIdx.x & (MBLK - 1), grp = threadIdx.x >> 6;
+  for (int mb = 0; mb * MBLK < ncol; ++mb) {
+    const int m = mb * MBLK + ml;
     double c = 0.0, s = 0.0;
-    if (m <= l) {
-      const int mb = m / MBLK, m_local = m % MBLK;
+    if (m <= l && m < ncol) {
       const int tile = t * q.ntiles + q.lb_first_tile[lb] + mb;
       const int b = q.tile_slot_begin[tile], e = q.tile_slot_begin[tile + 1];
-      for (int k = b; k < e; ++k) {
+#pragma unroll 4
+      for (int k = b + grp; k < e; k += 4) {
         const double* slot = q.slots + (size_t)k * SLOT_DOUBLES;
-        c += slot[(l_local)*MBLK + m_local];
-        s += slot[(LBLK + l_local) * MBLK + m_local];
+        c += slot[(l_local)*MBLK + ml];
+        s += slot[(LBLK + l_local) * MBLK + ml];
       }
-      c *= df;
-      s *= df;
     }
-    const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
-    q.clm[o] = c;
-    q.slm[o] = s;
+    part[0][grp][ml] = c;
+    part[1][grp][ml] = s;
+    __syncthreads();
+    if (grp == 0 && m < ncol) {
+      const double cc = ((part[0][0][ml] + part[0][1][ml]) + (part[0][2][ml] + part[0][3][ml])) * df;
+      const double ss = ((part[1][0][ml] + part[1][1][ml]) + (part[1][2][ml] + part[1][3][ml])) * df;
+      const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
+      q.clm[o] = (m <= l) ? cc : 0.0;
+      q.slm[o] = (m <= l) ? ss : 0.0;
+    }
+    __syncthreads();
   }
 }
 
@@ -611,10 +664,13 @@ int build_schedule(mhb200_plan* pl, int nbatch, int nlev, int mode) {
   for (int lb = 0; lb < pl->nlb; ++lb)
     for (int mb = 0; mb <= std::min(lb, pl->nmb - 1); ++mb)
       tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev)});
+  // per-unit cost = per-ring cost / nchunks (only ratios matter)
+  const int upr = pl->nchunks;                       // units per ring
+  const long long units_per_tile = (long long)pl->nlat * upr;
   double per_field = 0.0;
-  for (auto& tl : tiles) per_field += tl.c * pl->nlat;
+  for (auto& tl : tiles) per_field += tl.c * units_per_tile;
   const double total = per_field * nbatch;
-  const long long units = (long long)nbatch * (long long)tiles.size() * pl->nlat;
+  const long long units = (long long)nbatch * (long long)tiles.size() * units_per_tile;
   const int ncta = (int)std::min<long long>(pl->num_sms, units);
   std::vector<Segment> segs;
   std::vector<int> cta_begin(ncta + 1, 0);
@@ -625,19 +681,19 @@ int build_schedule(mhb200_plan* pl, int nbatch, int nlev, int mode) {
     for (size_t ti = 0; ti < tiles.size(); ++ti) {
       tile_slot_begin[(size_t)t * tiles.size() + ti] = (int)segs.size();
       const double c = tiles[ti].c;
-      int h = 0;
-      while (h < pl->nlat) {
-        // rings the current CTA can still take before its cost boundary
+      long long u = 0;
+      while (u < units_per_tile) {
+        // units the current CTA can still take before its cost boundary
         const double boundary = total * (double)(cta + 1) / (double)ncta;
-        int take = (int)std::floor((boundary - done) / c + 0.5);
-        if (cta == ncta - 1) take = pl->nlat - h;
-        take = std::max(0, std::min(take, pl->nlat - h));
+        long long take = (long long)std::floor((boundary - done) / c + 0.5);
+        if (cta == ncta - 1) take = units_per_tile - u;
+        take = std::max<long long>(0, std::min<long long>(take, units_per_tile - u));
         if (take > 0) {
-          segs.push_back({t, tiles[ti].lb, tiles[ti].mb, h, h + take, 0});
-          h += take;
+          segs.push_back({t, tiles[ti].lb, tiles[ti].mb, (int)u, (int)(u + take), 0});
+          u += take;
           done += take * c;
         }
-        if (h < pl->nlat && cta < ncta - 1) {   // this CTA is full: move to the next one
+        if (u < units_per_tile && cta < ncta - 1) {   // this CTA is full: move to the next one
           ++cta;
           cta_begin[cta] = (int)segs.size();
         }
@@ -722,7 +778,7 @@ int finish_reduce(mhb200_plan* pl, const double* dfactor, int nbatch, double* sl
   q.clm = clm;
   q.slm = slm;
   dim3 grid(pl->lmax + 1, nbatch);
-  stokes_reduce_kernel<<<grid, 64, 0, st>>>(q);
+  stokes_reduce_kernel<<<grid, 256, 0, st>>>(q);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());
   return MHB200_OK;
