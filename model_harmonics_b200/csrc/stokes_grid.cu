@@ -34,21 +34,28 @@
 
 namespace mhb {
 
-constexpr int NT = 256;           // threads per CTA
 constexpr int LBLK = 64;          // degrees per block
 constexpr int MBLK = 64;          // orders per block
-constexpr int KC_MAX = 128;       // longitudes per chunk (upper bound)
-constexpr int KS_MAX = KC_MAX / 4;
 constexpr int PLM_PITCH = 65;
 constexpr int CS_ROWS = 36;       // per-thread accumulators kept in shared memory
 constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
 constexpr int DF_MAX = 448;
-constexpr int LEV_GROUP = 40;      // levels staged per geometry pass
-// region 0 holds the B chunk (64 KB) and, before it is written, the staged (u0, r) pairs of the
-// atmosphere geometry pass (LEV_GROUP x 128 x 16 B = 80 KB)
-constexpr int REGION0_DOUBLES = LEV_GROUP * KC_MAX * 2;
-static_assert(REGION0_DOUBLES >= KS_MAX * 256, "region 0 must hold the B chunk");
-constexpr size_t SMEM_BYTES = (size_t)(REGION0_DOUBLES + CS_ROWS * NT + MBLK * PLM_PITCH) * sizeof(double);
+constexpr int LEV_GROUP = 40;     // levels staged per geometry pass
+
+// CTA shape.  NTH threads handle chunks of up to NTH/2 longitudes.  NTH = 256 runs one CTA per
+// SM; NTH = 128 runs two, so that one CTA's produce phase overlaps the other's contraction
+// phase on the shared fp64 pipe.
+template <int NTH>
+struct Shape {
+  static constexpr int KC = NTH / 2;             // longitudes per chunk (upper bound)
+  static constexpr int KS = KC / 4;              // k-steps per chunk (upper bound)
+  static constexpr int NW = NTH / 32;            // warps
+  // region 0 holds the B chunk (KC x 64 doubles) and, before it is written, the staged (u0, r)
+  // pairs of the atmosphere geometry pass (LEV_GROUP x KC x 16 B)
+  static constexpr int REGION0 = LEV_GROUP * KC * 2;
+  static_assert(REGION0 >= KS * 256, "region 0 must hold the B chunk");
+  static constexpr size_t SMEM = (size_t)(REGION0 + CS_ROWS * NTH + MBLK * PLM_PITCH) * sizeof(double);
+};
 
 enum Mode { MODE_PRESSURE = 0, MODE_ATM_BC05 = 1, MODE_ATM_SW02 = 2 };
 
@@ -164,12 +171,14 @@ __device__ __forceinline__ int bs_index(int l_local, int col) {
 
 // ---------------------------------------------------------------------------------------
 // Produce phase, pressure:  B[p,l] = (P/G) * (R/rad_e)^(l+2)   (gen_pressure_stokes.py:200)
-// A column is shared by the lane pair (lane, lane^16): each handles 32 of the 64 degrees.
+// A column is shared by two threads (warps w and w + NW/2): each handles 32 of the 64 degrees.
 // ---------------------------------------------------------------------------------------
+template <int NTH>
 __device__ __forceinline__ void produce_pressure(const GridParams& p, int t, int h, int lb, int chunk,
                                                  double* Bs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = warp * 16 + (lane & 15), half = lane >> 4;
+  constexpr int NWH = NTH / 64;
+  const int half = warp / NWH, col = (warp % NWH) * 32 + lane;
   if (col >= p.kc) return;
   const int pcol = chunk * p.kc + col;
   double f = 0.0, r = 1.0;
@@ -189,42 +198,71 @@ __device__ __forceinline__ void produce_pressure(const GridParams& p, int t, int
   }
 }
 
-// Branch-free fp64 reciprocal and square root (Newton from the fp32 SFU seed).  The library
-// sqrt()/division carry special-case branches that split the basic block and serialise the
-// geometry chain; operands here are always normal and far from the range limits.
-__device__ __forceinline__ double fast_rcp(double a) {
-  double y = (double)__frcp_rn((float)a);
-  double e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-a, y, 1.0);
-  return fma(y, e, y);
+// Branch-free fp64 reciprocal and square root: Newton/Goldschmidt from the fp64 SFU seeds
+// (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20).  The library sqrt()/division carry special-case
+// branches that split the basic block and serialise the geometry chain; operands here are
+// always normal and far from the range limits.  Everything is written W elements wide, one
+// statement at a time across the W independent elements, so that the instruction stream
+// itself carries the ILP needed to cover the 8-cycle DFMA latency at 2 warps per scheduler.
+constexpr int GW = 4;
+
+__device__ __forceinline__ void rcp_w(const double (&a)[GW], double (&y)[GW]) {
+#pragma unroll
+  for (int i = 0; i < GW; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(a[i]));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    double e[GW];
+#pragma unroll
+    for (int i = 0; i < GW; ++i) e[i] = fma(-a[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < GW; ++i) y[i] = fma(y[i], e[i], y[i]);
+  }
 }
-__device__ __forceinline__ double fast_div(double n, double d) {
-  const double y = fast_rcp(d);
-  const double q = n * y;
-  return fma(fma(-d, q, n), y, q);      // one correction step: within 1 ulp
+// q = n / d, within 1 ulp
+__device__ __forceinline__ void div_w(const double (&n)[GW], const double (&d)[GW], double (&q)[GW]) {
+  double y[GW], r[GW];
+  rcp_w(d, y);
+#pragma unroll
+  for (int i = 0; i < GW; ++i) q[i] = n[i] * y[i];
+#pragma unroll
+  for (int i = 0; i < GW; ++i) r[i] = fma(-d[i], q[i], n[i]);
+#pragma unroll
+  for (int i = 0; i < GW; ++i) q[i] = fma(r[i], y[i], q[i]);
 }
-__device__ __forceinline__ double fast_sqrt(double a) {
-  const double y = (double)rsqrtf((float)a);
-  double g = a * y, h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  return fma(fma(-g, g, a), h, g);
+__device__ __forceinline__ void sqrt_w(const double (&a)[GW], double (&g)[GW]) {
+  double h[GW], r[GW];
+#pragma unroll
+  for (int i = 0; i < GW; ++i) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a[i]));
+    g[i] = a[i] * y;
+    h[i] = 0.5 * y;
+  }
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+#pragma unroll
+    for (int i = 0; i < GW; ++i) r[i] = fma(-g[i], h[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < GW; ++i) g[i] = fma(g[i], r[i], g[i]);
+#pragma unroll
+    for (int i = 0; i < GW; ++i) h[i] = fma(h[i], r[i], h[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < GW; ++i) r[i] = fma(-g[i], g[i], a[i]);
+#pragma unroll
+  for (int i = 0; i < GW; ++i) g[i] = fma(r[i], h[i], g[i]);
 }
 
-// One level's contribution to the 32 degrees this thread owns:  acc[j] += u * r^j.
+// One level's contribution to the 32 degrees this thread owns:  acc[j] += u * r^(j + 32*UPPER).
 // Stride-8 scheme: 7 powers + per stride one add and seven FMAs
 // (~1.25 fp64-pipe slots per degree instead of 2 for "acc += t; t *= r").
-__device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, double r, int half) {
+template <bool UPPER>
+__device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, double r) {
   const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
   const double r5 = r4 * r, r6 = r4 * r2, r7 = r4 * r3, r8 = r4 * r4;
-  const double r16 = r8 * r8, r32 = r16 * r16;
+  const double r16 = r8 * r8;
   double us[4];
-  us[0] = u * (half ? r32 : 1.0);
+  us[0] = UPPER ? u * (r16 * r16) : u;
   us[1] = us[0] * r8;
   us[2] = us[0] * r16;
   us[3] = us[1] * r16;
@@ -242,35 +280,53 @@ __device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, do
   }
 }
 
-// per-column constants of the atmosphere geometry
+// per-column / per-ring constants of the atmosphere geometry
 struct ColumnGeom {
   double NG, NG1, cphi, sphi, geo_over;
+  double a1, a2, st, ct, gs, c1, rad_e, inv_rad;
 };
 
-// (u0, r) of one (level, column) element: u0 = -(dp/gamma) r^2 (BC05) or -(dp/g0) r^4 (SW02)
+// (u0, r) of GW (level, column) elements: u0 = -(dp/gamma) r^2 (BC05) or -(dp/g0) r^4 (SW02)
 template <int MODE>
-__device__ __forceinline__ double2 level_element(double z, double dpv, const ColumnGeom& c, double a1, double a2,
-                                                 double st, double ct, double gs, double c1, double rad_e,
-                                                 double inv_rad) {
-  double u0, r;
+__device__ __forceinline__ void level_elements(const double (&z)[GW], const double (&dpv)[GW],
+                                               const ColumnGeom& c, double (&u0)[GW], double (&r)[GW]) {
   if (MODE == MODE_ATM_BC05) {
-    const double H = a1 * z + a2 * (z * z);                 // orthometric height (List 1958), :222-224
-    const double A = c.NG + H, B = c.NG1 + H;
-    const double As = A * st;
-    const double X = As * c.cphi, Y = As * c.sphi, Z = B * ct;
-    const double R = fast_sqrt(fma(Z, Z, fma(Y, Y, X * X))); // :226-230
-    r = R * inv_rad;
-    const double hr = H * inv_rad;
-    const double gam = gs * fma(3.0 * hr, hr, fma(-c1, hr, 1.0));   // :232-238
-    const double q = fast_div(dpv, gam);
-    u0 = -(q * r) * r;
+    double H[GW], S[GW], R[GW], gam[GW], q[GW];
+#pragma unroll
+    for (int i = 0; i < GW; ++i) H[i] = c.a1 * z[i] + c.a2 * (z[i] * z[i]);   // orthometric height, :222-224
+#pragma unroll
+    for (int i = 0; i < GW; ++i) {
+      const double A = c.NG + H[i], B = c.NG1 + H[i];
+      const double As = A * c.st;
+      const double X = As * c.cphi, Y = As * c.sphi, Z = B * c.ct;
+      S[i] = fma(Z, Z, fma(Y, Y, X * X));                    // :226-230
+      const double hr = H[i] * c.inv_rad;
+      gam[i] = c.gs * fma(3.0 * hr, hr, fma(-c.c1, hr, 1.0));   // :232-238
+    }
+    sqrt_w(S, R);
+    div_w(dpv, gam, q);
+#pragma unroll
+    for (int i = 0; i < GW; ++i) {
+      r[i] = R[i] * c.inv_rad;
+      u0[i] = -(q[i] * r[i]) * r[i];
+    }
   } else {
-    r = fast_div(rad_e, rad_e - z) + c.geo_over;            // :258-260
-    const double q = fast_div(dpv, 9.80665);
-    const double r2 = r * r;
-    u0 = -(q * r2) * r2;
+    double den[GW], num[GW], t[GW], q[GW], g0[GW];
+#pragma unroll
+    for (int i = 0; i < GW; ++i) {
+      den[i] = c.rad_e - z[i];
+      num[i] = c.rad_e;
+      g0[i] = 9.80665;
+    }
+    div_w(num, den, t);                                      // :258-260
+    div_w(dpv, g0, q);
+#pragma unroll
+    for (int i = 0; i < GW; ++i) {
+      r[i] = t[i] + c.geo_over;
+      const double r2 = r[i] * r[i];
+      u0[i] = -(q[i] * r2) * r2;
+    }
   }
-  return make_double2(u0, r);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -279,92 +335,119 @@ __device__ __forceinline__ double2 level_element(double z, double dpv, const Col
 //   B[p,l] = - sum_k (dp_k/g0) (rad_e/(rad_e-GPH_k) + GEOID/rad_e)^(l+4)   SW02
 // (the minus sign is the reference's einsum(m_phi, -pfactor), :270).
 // Two passes per group of LEV_GROUP levels:
-//   geometry pass   : elementwise over (level, column), coalesced along lon, 4 independent
+//   geometry pass   : elementwise over (level, column), coalesced along lon, 8 independent
 //                     elements in flight per thread; (u0, r) staged in shared memory
-//   accumulate pass : lane pair (lane, lane^16) shares a column and splits the 64 degrees;
+//   accumulate pass : two threads (warps w, w + NW/2) share a column and split the 64 degrees;
 //                     32 running sums per thread in registers
 // ---------------------------------------------------------------------------------------
-template <int MODE, typename Tin>
+template <int MODE, typename Tin, int NTH>
 __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, int h, int lb, int chunk,
                                                    double* Bs) {
+  constexpr int KC = Shape<NTH>::KC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double2* stg = reinterpret_cast<double2*>(Bs);            // [level in group][128 columns]
+  double2* stg = reinterpret_cast<double2*>(Bs);            // [level in group][KC columns]
   const size_t lev_stride = (size_t)p.nlat * p.nlon;
   const int nlev = p.nlev;
-  const double inv_rad = 1.0 / p.rad_e;
   double sg = 1.0, sp = 1.0;
   if (p.field_scale != nullptr) {
     sg = p.field_scale[2 * t];
     sp = p.field_scale[2 * t + 1];
   }
-  // ring (colatitude-only) factors, built on the host
-  const double a1 = p.ring_tab[0 * p.nlat + h], a2 = p.ring_tab[1 * p.nlat + h];
-  const double st = p.ring_tab[4 * p.nlat + h], ct = p.ring_tab[5 * p.nlat + h];
-  const double gs = p.ring_tab[6 * p.nlat + h], c1 = p.ring_tab[7 * p.nlat + h];
-
-  // geometry-pass ownership: a fixed column, levels of parity tid>>7
-  const int gcol = tid & (KC_MAX - 1), gpar = tid >> 7;
+  // geometry-pass ownership: a fixed column, levels of parity tid / KC
+  const int gcol = tid & (KC - 1), gpar = tid / KC;
   const int gpcol = chunk * p.kc + gcol;
   const bool gactive = (gcol < p.kc) && (gpcol < p.nlon);
   const int gpc = gactive ? gpcol : 0;
   ColumnGeom cg;
   {
+    // ring (colatitude-only) factors built on the host; geoid per column
     const double geo = (p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + gpc * p.geo_s1) : 0.0;
+    cg.a1 = p.ring_tab[0 * p.nlat + h];
+    cg.a2 = p.ring_tab[1 * p.nlat + h];
     cg.NG = p.ring_tab[2 * p.nlat + h] + geo;     // (N + GEOID)
     cg.NG1 = p.ring_tab[3 * p.nlat + h] + geo;    // (N(1-e^2) + GEOID)
+    cg.st = p.ring_tab[4 * p.nlat + h];
+    cg.ct = p.ring_tab[5 * p.nlat + h];
+    cg.gs = p.ring_tab[6 * p.nlat + h];
+    cg.c1 = p.ring_tab[7 * p.nlat + h];
     cg.cphi = p.lon_tab[gpc];
     cg.sphi = p.lon_tab[p.nlon + gpc];
+    cg.rad_e = p.rad_e;
+    cg.inv_rad = 1.0 / p.rad_e;
     cg.geo_over = geo / p.rad_e;
   }
-  const Tin* zp = (const Tin*)p.GPH + (size_t)t * p.batch_stride + (size_t)h * p.nlon + gpc;
-  const Tin* dp = (const Tin*)p.dP + (size_t)t * p.batch_stride + (size_t)h * p.nlon + gpc;
+  const size_t col0 = (size_t)t * p.batch_stride + (size_t)h * p.nlon + gpc;
+  const Tin* zp = (const Tin*)p.GPH + col0;
+  const Tin* dp = (const Tin*)p.dP + col0;
 
-  // accumulate-pass ownership
-  const int acol = warp * 16 + (lane & 15), half = lane >> 4;
+  // accumulate-pass ownership: the lower half of the warps takes degrees 0..31 of a column,
+  // the upper half degrees 32..63 (warp-uniform, so the upper warps alone pay for r^32)
+  constexpr int NWH = NTH / 64;
+  const int half = warp / NWH;
+  const int acol = (warp % NWH) * 32 + lane;
   double acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.0;
 
   for (int kg = 0; kg < nlev; kg += LEV_GROUP) {
     const int ng = min(LEV_GROUP, nlev - kg);
-    // ---- geometry pass (loads of the next 4 elements are in flight while 4 are computed)
-    double zc[4], dc[4];
-    auto load4 = [&](double(&z)[4], double(&d)[4], int kk0) {
+    // ---- geometry pass: this thread's levels are kg + gpar + 2*i; batches of 4 with the next
+    //      batch's loads in flight (two register sets, loop unrolled by two batches)
+    const int nmine = (ng - gpar + 1) >> 1;
+    const Tin* zq = zp + (size_t)(kg + gpar) * lev_stride;
+    const Tin* dq = dp + (size_t)(kg + gpar) * lev_stride;
+    const size_t step2 = 2 * lev_stride;
+    auto load4 = [&](double(&z)[4], double(&d)[4], int i0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int kk = kk0 + 2 * i;
         z[i] = 0.0;
         d[i] = 0.0;
-        if (gactive && kk < ng) {
-          z[i] = ld_as_double(zp + (size_t)(kg + kk) * lev_stride);
-          d[i] = ld_as_double(dp + (size_t)(kg + kk) * lev_stride);
+        if (gactive && i0 + i < nmine) {
+          z[i] = ld_as_double(zq + (size_t)(i0 + i) * step2);
+          d[i] = ld_as_double(dq + (size_t)(i0 + i) * step2);
         }
       }
     };
-    load4(zc, dc, gpar);
-    for (int kk0 = gpar; kk0 < ng; kk0 += 8) {
-      double zn[4], dn[4];
-      load4(zn, dn, kk0 + 8);
+    auto compute4 = [&](const double(&z)[4], const double(&d)[4], int i0) {
+      double zs[4], ds[4], u0[4], r[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int kk = kk0 + 2 * i;
-        double2 e = level_element<MODE>(sg * zc[i], sp * dc[i], cg, a1, a2, st, ct, gs, c1, p.rad_e, inv_rad);
-        if (lb > 0) e.x *= ipow(e.y, lb * LBLK);
-        if (!gactive) e = make_double2(0.0, 1.0);
-        if (kk < ng) stg[kk * KC_MAX + gcol] = e;
+        zs[i] = sg * z[i];
+        ds[i] = sp * d[i];
       }
+      level_elements<MODE>(zs, ds, cg, u0, r);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        zc[i] = zn[i];
-        dc[i] = dn[i];
+        if (lb > 0) u0[i] *= ipow(r[i], lb * LBLK);
+        if (!gactive) {
+          u0[i] = 0.0;
+          r[i] = 1.0;
+        }
+        if (i0 + i < nmine) stg[(gpar + 2 * (i0 + i)) * KC + gcol] = make_double2(u0[i], r[i]);
       }
+    };
+    double zA[4], dA[4], zB[4], dB[4];
+    load4(zA, dA, 0);
+    for (int i0 = 0; i0 < nmine; i0 += 8) {
+      load4(zB, dB, i0 + 4);
+      compute4(zA, dA, i0);
+      load4(zA, dA, i0 + 8);
+      compute4(zB, dB, i0 + 4);
     }
     __syncthreads();
     // ---- accumulate pass
+    if (half) {
 #pragma unroll 2
-    for (int kk = 0; kk < ng; ++kk) {
-      const double2 e = stg[kk * KC_MAX + acol];
-      accumulate_level(acc, e.x, e.y, half);
+      for (int kk = 0; kk < ng; ++kk) {
+        const double2 e = stg[kk * KC + acol];
+        accumulate_level<true>(acc, e.x, e.y);
+      }
+    } else {
+#pragma unroll 2
+      for (int kk = 0; kk < ng; ++kk) {
+        const double2 e = stg[kk * KC + acol];
+        accumulate_level<false>(acc, e.x, e.y);
+      }
     }
     __syncthreads();      // staging is overwritten by the next group / by the B chunk
   }
@@ -377,14 +460,14 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 
 // L2 prefetch of the cube data the next chunk's geometry pass will read (issued before the
 // contraction phase so that DRAM latency is off the critical path)
-template <typename Tin>
+template <typename Tin, int NTH>
 __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
   if (h >= p.nlat) return;
   const size_t lev_stride = (size_t)p.nlat * p.nlon;
   const int per_line = 128 / (int)sizeof(Tin);
   const int lines = (p.kc + per_line - 1) / per_line + 1;
   const size_t base = (size_t)t * p.batch_stride + (size_t)h * p.nlon + (size_t)chunk * p.kc;
-  for (int i = threadIdx.x; i < p.nlev * lines * 2; i += NT) {
+  for (int i = threadIdx.x; i < p.nlev * lines * 2; i += NTH) {
     const int arr = i & 1, j = i >> 1;
     const int k = j / lines, ln = j % lines;
     const int col = min(ln * per_line, p.kc - 1);
@@ -398,46 +481,32 @@ __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h
 // One segment: work units [u0, u1) (unit = ring * nchunks + chunk) of tile (lb, mb) of field t.
 //
 // DIAG tile (lb == mb): only the 8x8 sub-tiles with degree-tile >= order-tile are needed (36 of
-// 64).  The four warps {q, q+4} ... share the order groups gA = q and gB = 7-q, i.e. 9
-// (order-group, degree-tile) pairs j = 0..8.  Warp q owns pairs 0..3, warp q+4 owns pairs 5..8,
-// and the "swing" pair 4 is done by warp q on even k-steps and by warp q+4 on odd k-steps:
-// 9 DMMA pairs per two k-steps for every warp (perfectly balanced), 5 accumulator pairs per
-// thread.  FULL tile: warp w owns order group w and all 8 degree tiles.
+// 64).  Order groups are paired (g, 7-g): 9 (order-group, degree-tile) sub-tiles per pair,
+// balanced.  Warp w takes pair w & 3; with 8 warps the two warps of a pair split the k-steps
+// by parity (w >> 2), with 4 warps each warp takes every k-step.
+// FULL tile (8 warps only): warp w owns order group w and all 8 degree tiles.
 // ---------------------------------------------------------------------------------------
-#ifndef MHB_SWING
-#define MHB_SWING 0
-#endif
-template <int MODE, typename Tin, bool DIAG>
+template <int MODE, typename Tin, bool DIAG, int NTH>
 __device__ __forceinline__ void run_segment(const GridParams& p, const Segment seg, int slot_index,
                                             double* Bs, double* Cs, double* plm_s) {
-  // SW = swing mapping (above); !SW = each warp of a quad does all 9 pairs on k-steps of one parity
-  constexpr bool SW = (MHB_SWING != 0);
-  constexpr int NP = DIAG ? (SW ? 5 : 9) : 8;          // accumulator pairs per thread
-  constexpr int KSTRIDE = (DIAG && !SW) ? 2 : 1;
-  constexpr int NA = DIAG ? 4 : 2;          // trig fragments per k-step
+  constexpr int NW = Shape<NTH>::NW;
+  static_assert(DIAG || NW == 8, "FULL tiles need the 8-warp shape");
+  constexpr int NP = DIAG ? 9 : 8;               // accumulator pairs per thread
+  constexpr int NA = DIAG ? 4 : 2;               // trig fragments per k-step
+  constexpr int KSTRIDE = (DIAG && NW == 8) ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sub = DIAG ? (warp >> 2) : 0;
+  const int sub = (DIAG && NW == 8) ? (warp >> 2) : 0;
   const int gA = DIAG ? (warp & 3) : warp;
   const int gB = DIAG ? (7 - gA) : warp;
   const int nA = DIAG ? (8 - gA) : 8;
   const int nksc = p.kc >> 2;
 
-  int lt[NP];          // degree tile of local pair j
-  bool inA[NP];        // pair belongs to order group gA (else gB)
+  int lt[NP];          // degree tile of pair j
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    if (DIAG) {
-      const int jg = SW ? ((j < 4) ? (sub ? 5 + j : j) : 4) : j;     // index in the quad's list of 9 pairs
-      inA[j] = (jg < nA);
-      lt[j] = inA[j] ? (gA + jg) : (jg - 1);
-    } else {
-      inA[j] = true;
-      lt[j] = j;
-    }
-  }
+  for (int j = 0; j < NP; ++j) lt[j] = DIAG ? ((j < nA) ? (gA + j) : (j - 1)) : j;
 
 #pragma unroll
-  for (int i = 0; i < NP * 4; ++i) Cs[i * NT + tid] = 0.0;
+  for (int i = 0; i < NP * 4; ++i) Cs[i * NTH + tid] = 0.0;
 
   const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
   for (int h = hfirst; h <= hlast; ++h) {
@@ -453,57 +522,65 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
     for (int chunk = cbeg; chunk < cend; ++chunk) {
       if (MODE == MODE_PRESSURE)
-        produce_pressure(p, seg.t, h, seg.lb, chunk, Bs);
+        produce_pressure<NTH>(p, seg.t, h, seg.lb, chunk, Bs);
       else
-        produce_atmosphere<MODE, Tin>(p, seg.t, h, seg.lb, chunk, Bs);
+        produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs);
       __syncthreads();
 
       if (MODE != MODE_PRESSURE) {
         // start pulling the next chunk's (or next ring's first chunk's) cube data into L2
         const bool last = (chunk + 1 == p.nchunks);
-        prefetch_chunk<Tin>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        prefetch_chunk<Tin, NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }
       // contraction over the chunk's longitudes; trig fragments straight from L2 (fragment-major
       // table: one coalesced 256-byte load per fragment, prefetched three k-steps ahead in a
-      // register ring), B fragments from shared memory
+      // register ring), B fragments from shared memory one k-step ahead
       const double* Ablk = p.trig + ((size_t)(seg.mb * p.nks_total + chunk * nksc) * 16) * 32 + lane;
       auto load_a = [&](double(&a)[NA], int k) {
         if (k < nksc) {
           const double* ap = Ablk + (size_t)k * 512;
           a[0] = __ldg(ap + (gA * 2) * 32);
           a[1] = __ldg(ap + (gA * 2 + 1) * 32);
-          if (DIAG && (sub || !SW)) {        // swing: only the second warp of a quad touches order group gB
+          if (DIAG) {
             a[2] = __ldg(ap + (gB * 2) * 32);
             a[3] = __ldg(ap + (gB * 2 + 1) * 32);
           }
         }
       };
-      double a[4][NA];
+      const int brot = lane >> 2, bcol = lane & 3;
+      auto load_b = [&](double(&b)[NP], int k) {
+        if (k < nksc) {
+          const double* Bk = Bs + k * 256 + (((brot + k) & 7) << 2) + bcol;
+#pragma unroll
+          for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
+        }
+      };
+      double a[4][NA], b[2][NP];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < NA; ++j) a[i][j] = 0.0;
-      const int k0 = (DIAG && !SW) ? sub : 0;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) b[0][j] = b[1][j] = 0.0;
+      const int k0 = sub;
 #pragma unroll
       for (int i = 0; i < 3; ++i) load_a(a[i], k0 + i * KSTRIDE);
-      // 4-deep ring, fully unrolled so no rotation copies shorten the prefetch distance;
-      // with stride 1 the k-step parity of ring slot u is u & 1 (compile time)
+      load_b(b[0], k0);
+      // 4-deep trig ring / 2-deep B ring, fully unrolled: no rotation copies
       for (int ks = k0; ks < nksc; ks += 4 * KSTRIDE) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int k = ks + u * KSTRIDE;
           if (k < nksc) {
             load_a(a[(u + 3) & 3], k + 3 * KSTRIDE);
+            load_b(b[(u + 1) & 1], k + KSTRIDE);
             const double(&c)[NA] = a[u];
-            const double* Bk = Bs + k * 256 + ((((lane >> 2) + k) & 7) << 2) + (lane & 3);
-            double b[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
+            const double(&bb)[NP] = b[u & 1];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-              if (DIAG && SW && j == 4 && ((u & 1) != sub)) continue;     // swing pair: other warp's turn
-              dmma884(acc[j][0][0], acc[j][0][1], inA[j] ? c[0] : c[DIAG ? 2 : 0], b[j]);
-              dmma884(acc[j][1][0], acc[j][1][1], inA[j] ? c[1] : c[DIAG ? 3 : 1], b[j]);
+              const bool first = (!DIAG) || (j < nA);
+              dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], bb[j]);
+              dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], bb[j]);
             }
           }
         }
@@ -514,16 +591,16 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
     // ring epilogue: C += (w_h Plm) o Dring
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      const int g = inA[j] ? gA : gB;
+      const int g = ((!DIAG) || (j < nA)) ? gA : gB;
       const int m_local = g * 8 + (lane >> 2);
       const int l_local = lt[j] * 8 + 2 * (lane & 3);
       const double w0 = plm_s[m_local * PLM_PITCH + l_local];
       const double w1 = plm_s[m_local * PLM_PITCH + l_local + 1];
 #pragma unroll
       for (int cs = 0; cs < 2; ++cs) {
-        double* c = Cs + ((j * 2 + cs) * 2) * NT + tid;
+        double* c = Cs + ((j * 2 + cs) * 2) * NTH + tid;
         c[0] = fma(w0, acc[j][cs][0], c[0]);
-        c[NT] = fma(w1, acc[j][cs][1], c[NT]);
+        c[NTH] = fma(w1, acc[j][cs][1], c[NTH]);
       }
     }
     __syncthreads();
@@ -531,40 +608,41 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
   // write the segment's partial sums: slot[cs][l_local][m_local]
   double* slot = p.slots + (size_t)slot_index * SLOT_DOUBLES;
+  if (KSTRIDE == 1 || sub == 0) {
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    if (DIAG && SW && j == 4 && sub) continue;        // the swing pair is written by the first warp
-    if (DIAG && !SW && sub) continue;             // parity mapping: first warp writes the sum of both
-    const int g = inA[j] ? gA : gB;
-    const int m_local = g * 8 + (lane >> 2);
-    const int l_local = lt[j] * 8 + 2 * (lane & 3);
+    for (int j = 0; j < NP; ++j) {
+      const int g = ((!DIAG) || (j < nA)) ? gA : gB;
+      const int m_local = g * 8 + (lane >> 2);
+      const int l_local = lt[j] * 8 + 2 * (lane & 3);
 #pragma unroll
-    for (int cs = 0; cs < 2; ++cs) {
+      for (int cs = 0; cs < 2; ++cs) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int row = ((j * 2 + cs) * 2 + e) * NT;
-        double v = Cs[row + tid];
-        if (DIAG && (j == 4 || !SW)) v += Cs[row + tid + 128];   // even + odd k-steps
-        slot[(cs * LBLK + l_local + e) * MBLK + m_local] = v;
+        for (int e = 0; e < 2; ++e) {
+          const int row = ((j * 2 + cs) * 2 + e) * NTH;
+          double v = Cs[row + tid];
+          if (KSTRIDE == 2) v += Cs[row + tid + 128];   // the two k-parities
+          slot[(cs * LBLK + l_local + e) * MBLK + m_local] = v;
+        }
       }
     }
   }
   __syncthreads();
 }
 
-template <int MODE, typename Tin>
-__global__ void __launch_bounds__(NT, 1) stokes_ring_kernel(const GridParams p) {
+template <int MODE, typename Tin, int NTH>
+__global__ void __launch_bounds__(NTH, 256 / NTH) stokes_ring_kernel(const GridParams p) {
   extern __shared__ double smem[];
   double* Bs = smem;
-  double* Cs = Bs + REGION0_DOUBLES;
-  double* plm_s = Cs + CS_ROWS * NT;
+  double* Cs = Bs + Shape<NTH>::REGION0;
+  double* plm_s = Cs + CS_ROWS * NTH;
   const int sb = p.cta_seg_begin[blockIdx.x], se = p.cta_seg_begin[blockIdx.x + 1];
   for (int s = sb; s < se; ++s) {
     const Segment seg = p.segs[s];
-    if (seg.lb == seg.mb)
-      run_segment<MODE, Tin, true>(p, seg, s, Bs, Cs, plm_s);
-    else
-      run_segment<MODE, Tin, false>(p, seg, s, Bs, Cs, plm_s);
+    if (seg.lb == seg.mb) {
+      run_segment<MODE, Tin, true, NTH>(p, seg, s, Bs, Cs, plm_s);
+    } else {
+      if constexpr (NTH == 256) run_segment<MODE, Tin, false, NTH>(p, seg, s, Bs, Cs, plm_s);
+    }
   }
 }
 
@@ -620,19 +698,26 @@ struct Schedule {
   int* tile_slot_begin_dev = nullptr;
 };
 
+// longitude chunking + trig table for one CTA shape (variant 0: 256 threads, 1: 128 threads)
+struct Variant {
+  int nth = 0, ctas_per_sm = 1;
+  int kc = 0, nchunks = 0, nks_total = 0;
+  double* trig = nullptr;
+  Schedule sched;
+};
+
 struct mhb200_plan {
   int device, nlat, nlon, lmax, mmax;
-  int nlb, nmb, Mpad, ntiles;
-  int kc, nchunks, nks_total, num_sms;
-  double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
+  int nlb, nmb, Mpad, ntiles, num_sms;
+  Variant var[2];
+  double *f1, *f2, *pmm, *sq, *rescale, *x, *w;
   int* lb_first_tile_dev;
   std::vector<int> lb_first_tile;
-  // per-call staging (dfactor, field scales), grown on demand
+  // per-call staging (field scales, long degree-factor vectors), grown on demand
   double* stage_dev;
   size_t stage_doubles;
   size_t stage_reserved;   // doubles at the front of the staging buffer used by field scales
   std::mutex mu;
-  Schedule sched;
 };
 
 namespace {
@@ -651,27 +736,32 @@ double ring_cost(bool diag, int mode, int nlev) {
   return mma + prod;
 }
 
-int build_schedule(mhb200_plan* pl, int nbatch, int nlev, int mode) {
-  Schedule& sc = pl->sched;
-  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode) return MHB200_OK;
+void free_schedule(Schedule& sc) {
   if (sc.segs_dev) cudaFree(sc.segs_dev);
   if (sc.cta_seg_begin_dev) cudaFree(sc.cta_seg_begin_dev);
   if (sc.tile_slot_begin_dev) cudaFree(sc.tile_slot_begin_dev);
   sc = Schedule();
-  // linearised work: (field, tile, ring) with per-ring cost
+}
+
+// Static schedule: the (field, tile, ring, chunk) work units are linearised and cut into
+// contiguous spans of equal cost, one span per CTA; a span is split into segments at tile
+// boundaries, and every segment owns one partial-sum slot.
+int build_schedule(mhb200_plan* pl, Variant& v, int nbatch, int nlev, int mode) {
+  Schedule& sc = v.sched;
+  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode) return MHB200_OK;
+  free_schedule(sc);
   struct Tile { int lb, mb; double c; };
   std::vector<Tile> tiles;
   for (int lb = 0; lb < pl->nlb; ++lb)
     for (int mb = 0; mb <= std::min(lb, pl->nmb - 1); ++mb)
       tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev)});
   // per-unit cost = per-ring cost / nchunks (only ratios matter)
-  const int upr = pl->nchunks;                       // units per ring
-  const long long units_per_tile = (long long)pl->nlat * upr;
+  const long long units_per_tile = (long long)pl->nlat * v.nchunks;
   double per_field = 0.0;
   for (auto& tl : tiles) per_field += tl.c * units_per_tile;
   const double total = per_field * nbatch;
   const long long units = (long long)nbatch * (long long)tiles.size() * units_per_tile;
-  const int ncta = (int)std::min<long long>(pl->num_sms, units);
+  const int ncta = (int)std::min<long long>((long long)pl->num_sms * v.ctas_per_sm, units);
   std::vector<Segment> segs;
   std::vector<int> cta_begin(ncta + 1, 0);
   std::vector<int> tile_slot_begin((size_t)nbatch * tiles.size() + 1, 0);
@@ -721,7 +811,18 @@ int build_schedule(mhb200_plan* pl, int nbatch, int nlev, int mode) {
 
 size_t max_segments(const mhb200_plan* pl, int nbatch) {
   // every (field, tile) contributes at least one segment and every CTA boundary at most one more
-  return (size_t)nbatch * pl->ntiles + pl->num_sms + 1;
+  return (size_t)nbatch * pl->ntiles + 2 * (size_t)pl->num_sms + 1;
+}
+
+// CTA shape for a call.  128-thread CTAs (two per SM) only cover single-block problems
+// (LMAX <= 63); MHB200_NT=128|256 forces a shape where legal.
+int pick_variant(const mhb200_plan* pl, int mode) {
+  int v = (pl->nlb == 1 && mode != MODE_PRESSURE) ? 1 : 0;
+  if (const char* e = getenv("MHB200_NT")) {
+    if (atoi(e) == 256) v = 0;
+    if (atoi(e) == 128 && pl->nlb == 1) v = 1;
+  }
+  return v;
 }
 
 int stage(mhb200_plan* pl, const double* host, size_t n, size_t offset, cudaStream_t st) {
@@ -746,18 +847,24 @@ int ensure_stage(mhb200_plan* pl, size_t n) {
   return MHB200_OK;
 }
 
-template <int MODE, typename Tin>
-int launch_ring(const GridParams& gp, int ncta, cudaStream_t st) {
-  auto kern = stokes_ring_kernel<MODE, Tin>;
-  MHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  kern<<<ncta, NT, SMEM_BYTES, st>>>(gp);
+template <int MODE, typename Tin, int NTH>
+int launch_ring_shape(const GridParams& gp, int ncta, cudaStream_t st) {
+  auto kern = stokes_ring_kernel<MODE, Tin, NTH>;
+  MHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<NTH>::SMEM));
+  kern<<<ncta, NTH, Shape<NTH>::SMEM, st>>>(gp);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());
   return MHB200_OK;
 }
 
-int finish_reduce(mhb200_plan* pl, const double* dfactor, int nbatch, double* slots, double* clm, double* slm,
-                  cudaStream_t st) {
+template <int MODE, typename Tin>
+int launch_ring(const GridParams& gp, const Variant& v, cudaStream_t st) {
+  return (v.nth == 128) ? launch_ring_shape<MODE, Tin, 128>(gp, v.sched.ncta, st)
+                        : launch_ring_shape<MODE, Tin, 256>(gp, v.sched.ncta, st);
+}
+
+int finish_reduce(mhb200_plan* pl, const Variant& v, const double* dfactor, int nbatch, double* slots,
+                  double* clm, double* slm, cudaStream_t st) {
   ReduceParams q;
   q.dfactor_dev = nullptr;
   if (pl->lmax + 1 <= DF_MAX) {
@@ -772,7 +879,7 @@ int finish_reduce(mhb200_plan* pl, const double* dfactor, int nbatch, double* sl
   q.mmax = pl->mmax;
   q.nmb = pl->nmb;
   q.ntiles = pl->ntiles;
-  q.tile_slot_begin = pl->sched.tile_slot_begin_dev;
+  q.tile_slot_begin = v.sched.tile_slot_begin_dev;
   q.lb_first_tile = pl->lb_first_tile_dev;
   q.slots = slots;
   q.clm = clm;
@@ -784,17 +891,17 @@ int finish_reduce(mhb200_plan* pl, const double* dfactor, int nbatch, double* sl
   return MHB200_OK;
 }
 
-void fill_plan_params(const mhb200_plan* pl, GridParams& gp) {
+void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
   memset(&gp, 0, sizeof(gp));
   gp.nlat = pl->nlat;
   gp.nlon = pl->nlon;
   gp.lmax = pl->lmax;
   gp.mmax = pl->mmax;
   gp.Mpad = pl->Mpad;
-  gp.kc = pl->kc;
-  gp.nchunks = pl->nchunks;
-  gp.nks_total = pl->nks_total;
-  gp.trig = pl->trig;
+  gp.kc = v.kc;
+  gp.nchunks = v.nchunks;
+  gp.nks_total = v.nks_total;
+  gp.trig = v.trig;
   gp.f1 = pl->f1;
   gp.f2 = pl->f2;
   gp.pmm = pl->pmm;
@@ -802,8 +909,32 @@ void fill_plan_params(const mhb200_plan* pl, GridParams& gp) {
   gp.rescale = pl->rescale;
   gp.x = pl->x;
   gp.w = pl->w;
-  gp.segs = pl->sched.segs_dev;
-  gp.cta_seg_begin = pl->sched.cta_seg_begin_dev;
+  gp.segs = v.sched.segs_dev;
+  gp.cta_seg_begin = v.sched.cta_seg_begin_dev;
+}
+
+// trig table, fragment-major [mb][kstep][16 row tiles][32 lanes]  (m_phi, gen_pressure_stokes.py:176-177)
+int build_variant(mhb200_plan* pl, Variant& v, int nth, const double* phi) {
+  v.nth = nth;
+  v.ctas_per_sm = 256 / nth;
+  const int kcmax = nth / 2;
+  v.nchunks = (pl->nlon + kcmax - 1) / kcmax;
+  v.kc = (((pl->nlon + v.nchunks - 1) / v.nchunks) + 7) / 8 * 8;
+  v.nks_total = v.nchunks * (v.kc / 4);
+  std::vector<double> trig((size_t)pl->nmb * v.nks_total * 512, 0.0);
+  for (int mb = 0; mb < pl->nmb; ++mb)
+    for (int ks = 0; ks < v.nks_total; ++ks)
+      for (int g = 0; g < 8; ++g)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int m = mb * MBLK + g * 8 + (lane >> 2);
+          const int p = ks * 4 + (lane & 3);
+          if (m > pl->mmax || p >= pl->nlon) continue;
+          const double arg = (double)m * phi[p];
+          const size_t base = (((size_t)mb * v.nks_total + ks) * 16 + g * 2) * 32 + lane;
+          trig[base] = cos(arg);
+          trig[base + 32] = sin(arg);
+        }
+  return upload(&v.trig, trig);
 }
 
 }  // namespace
@@ -828,9 +959,6 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   pl->nlb = (lmax + LBLK) / LBLK;
   pl->nmb = (mmax + MBLK) / MBLK;
   pl->Mpad = pl->nmb * MBLK;
-  pl->nchunks = (nlon + KC_MAX - 1) / KC_MAX;
-  pl->kc = (((nlon + pl->nchunks - 1) / pl->nchunks) + 7) / 8 * 8;
-  pl->nks_total = pl->nchunks * (pl->kc / 4);
   pl->stage_dev = nullptr;
   pl->stage_doubles = 0;
   pl->stage_reserved = 0;
@@ -845,21 +973,9 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   }
   pl->ntiles = nt;
 
-  // trig table, fragment-major [mb][kstep][16 row tiles][32 lanes]  (m_phi, gen_pressure_stokes.py:176-177)
-  const int npad = pl->nks_total * 4;
-  std::vector<double> trig((size_t)pl->nmb * pl->nks_total * 512, 0.0);
-  for (int mb = 0; mb < pl->nmb; ++mb)
-    for (int ks = 0; ks < pl->nks_total; ++ks)
-      for (int g = 0; g < 8; ++g)
-        for (int lane = 0; lane < 32; ++lane) {
-          const int m = mb * MBLK + g * 8 + (lane >> 2);
-          const int p = ks * 4 + (lane & 3);
-          if (m > mmax || p >= nlon || p >= npad) continue;
-          const double arg = (double)m * phi[p];
-          const size_t base = (((size_t)mb * pl->nks_total + ks) * 16 + g * 2) * 32 + lane;
-          trig[base] = cos(arg);
-          trig[base + 32] = sin(arg);
-        }
+  if ((rc = build_variant(pl, pl->var[0], 256, phi)) != MHB200_OK) { delete pl; return rc; }
+  if (pl->nlb == 1 && (rc = build_variant(pl, pl->var[1], 128, phi)) != MHB200_OK) { delete pl; return rc; }
+
   // Holmes-Featherstone multipliers [(lmax+1)][Mpad], sectoral seeds and sqrt(2m+3)
   const int Mpad = pl->Mpad;
   std::vector<double> f1((size_t)(lmax + 1) * Mpad, 0.0), f2((size_t)(lmax + 1) * Mpad, 0.0);
@@ -897,10 +1013,9 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
       rescale[(size_t)h * Mpad + m] = r;
     }
   }
-  if ((rc = upload(&pl->trig, trig)) || (rc = upload(&pl->f1, f1)) || (rc = upload(&pl->f2, f2)) ||
-      (rc = upload(&pl->pmm, pmm)) || (rc = upload(&pl->sq, sq)) || (rc = upload(&pl->rescale, rescale)) ||
-      (rc = upload(&pl->x, xs)) || (rc = upload(&pl->w, ws)) ||
-      (rc = upload(&pl->lb_first_tile_dev, pl->lb_first_tile))) {
+  if ((rc = upload(&pl->f1, f1)) || (rc = upload(&pl->f2, f2)) || (rc = upload(&pl->pmm, pmm)) ||
+      (rc = upload(&pl->sq, sq)) || (rc = upload(&pl->rescale, rescale)) || (rc = upload(&pl->x, xs)) ||
+      (rc = upload(&pl->w, ws)) || (rc = upload(&pl->lb_first_tile_dev, pl->lb_first_tile))) {
     delete pl;
     return rc;
   }
@@ -911,7 +1026,10 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
 int mhb200_plan_destroy(mhb200_plan* pl) {
   if (!pl) return MHB200_OK;
   cudaSetDevice(pl->device);
-  cudaFree(pl->trig);
+  for (auto& v : pl->var) {
+    if (v.trig) cudaFree(v.trig);
+    free_schedule(v.sched);
+  }
   cudaFree(pl->f1);
   cudaFree(pl->f2);
   cudaFree(pl->pmm);
@@ -921,9 +1039,6 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   cudaFree(pl->w);
   cudaFree(pl->lb_first_tile_dev);
   if (pl->stage_dev) cudaFree(pl->stage_dev);
-  if (pl->sched.segs_dev) cudaFree(pl->sched.segs_dev);
-  if (pl->sched.cta_seg_begin_dev) cudaFree(pl->sched.cta_seg_begin_dev);
-  if (pl->sched.tile_slot_begin_dev) cudaFree(pl->sched.tile_slot_begin_dev);
   delete pl;
   return MHB200_OK;
 }
@@ -950,11 +1065,12 @@ int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const in
   std::lock_guard<std::mutex> lock(pl->mu);
   cudaStream_t st = (cudaStream_t)stream;
   MHB_CUDA(cudaSetDevice(pl->device));
+  Variant& v = pl->var[pick_variant(pl, MODE_PRESSURE)];
   int rc;
-  if ((rc = build_schedule(pl, nbatch, 0, MODE_PRESSURE)) != MHB200_OK) return rc;
+  if ((rc = build_schedule(pl, v, nbatch, 0, MODE_PRESSURE)) != MHB200_OK) return rc;
   pl->stage_reserved = 0;
   GridParams gp;
-  fill_plan_params(pl, gp);
+  fill_plan_params(pl, v, gp);
   gp.plm_table = plm_table;
   gp.slots = (double*)workspace;
   gp.P = P;
@@ -966,8 +1082,8 @@ int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const in
     gp.Rs[i] = Rs[i];
   }
   gp.rad_e = rad_e;
-  if ((rc = launch_ring<MODE_PRESSURE, double>(gp, pl->sched.ncta, st)) != MHB200_OK) return rc;
-  return finish_reduce(pl, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+  if ((rc = launch_ring<MODE_PRESSURE, double>(gp, v, st)) != MHB200_OK) return rc;
+  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
 }
 
 int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH, const void* dP,
@@ -991,14 +1107,15 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
   cudaStream_t st = (cudaStream_t)stream;
   MHB_CUDA(cudaSetDevice(pl->device));
   const int mode = (method == MHB200_METHOD_BC05) ? MODE_ATM_BC05 : MODE_ATM_SW02;
+  Variant& v = pl->var[pick_variant(pl, mode)];
   int rc;
-  if ((rc = build_schedule(pl, nbatch, nlev, mode)) != MHB200_OK) return rc;
+  if ((rc = build_schedule(pl, v, nbatch, nlev, mode)) != MHB200_OK) return rc;
   const size_t nl = (size_t)pl->lmax + 1;
   pl->stage_reserved = field_scale ? 2 * (size_t)nbatch : 0;
   if ((rc = ensure_stage(pl, nl + 2 * (size_t)nbatch)) != MHB200_OK) return rc;
   if (field_scale && (rc = stage(pl, field_scale, 2 * (size_t)nbatch, 0, st)) != MHB200_OK) return rc;
   GridParams gp;
-  fill_plan_params(pl, gp);
+  fill_plan_params(pl, v, gp);
   gp.plm_table = plm_table;
   gp.slots = (double*)workspace;
   gp.GPH = GPH;
@@ -1012,15 +1129,14 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
   gp.lon_tab = lon_tab;
   gp.nlev = nlev;
   gp.rad_e = rad_e;
-  const int ncta = pl->sched.ncta;
   if (mode == MODE_ATM_BC05)
-    rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_BC05, double>(gp, ncta, st)
-                               : launch_ring<MODE_ATM_BC05, float>(gp, ncta, st);
+    rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_BC05, double>(gp, v, st)
+                               : launch_ring<MODE_ATM_BC05, float>(gp, v, st);
   else
-    rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_SW02, double>(gp, ncta, st)
-                               : launch_ring<MODE_ATM_SW02, float>(gp, ncta, st);
+    rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_SW02, double>(gp, v, st)
+                               : launch_ring<MODE_ATM_SW02, float>(gp, v, st);
   if (rc != MHB200_OK) return rc;
-  return finish_reduce(pl, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
 }
 
 }  // extern "C"
