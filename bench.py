@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""
+bench.py -- fields -> Stokes coefficients per second (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port)
+
+Workload (config.workload = "atmosphere_c3"): ERA5-shaped 0.25 degree, 37-level atmospheric
+fields (37 x 721 x 1440, fp64) -> LMAX = 60 Stokes coefficients with gen_atmosphere_stokes'
+arithmetic (BASELINE.json configs[2]/[4]; the configuration the north star's target is quoted
+on).  A step is one pass of the hot path over a batch of --fields fields per GPU, each derived
+on load from one device-resident base cube by the IEEE-exact scalings of SURVEY.md 8(d)
+(GPH_t = GPH_0 (1+a_t), dP_t = dP_0 (1+b_t)); with N > 1 every rank takes its own time steps
+(weak scaling) and the step ends with the NCCL gather of the coefficient blocks.
+
+value   : whole-job fields/s with inputs resident in HBM (CUDA events, max over ranks).
+e2e     : the same metric through the drop-in Python call gen_atmosphere_stokes with HOST
+          (pinned) fp64 cubes: H2D of both cubes and D2H of the coefficients inside the timed
+          region, every field.
+roofline: algorithmic fp64 flops of SURVEY.md 8(d) per launch / device time of
+          stokes_ring_kernel (CUDA events on its own stream, inside the timed region) against
+          the measured fp64 DMMA peak (profiles/r01_fp64_peaks.jsonl; MEASURED_PEAKS.json has
+          no fp64 figure), plus the HBM view of the same launch.
+cpu_baseline / --impl reference: the NumPy oracle port of the reference's algorithm on the
+          box's host cores, process-parallel over time steps, on a bounded latitude sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NLEV, NLAT, NLON, LMAX = 37, 721, 1440, 60
+FP64_PEAK_TFLOPS = 37.0       # measured on this pool: DMMA m8n8k4 fp64 (profiles/r01_fp64_peaks.jsonl)
+SAMPLE_STRIDE = 8             # CPU arm: every 8th latitude ring (91 of 721)
+
+
+def algorithmic_flops_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON, L=LMAX):
+    """F_atm = nlev nlat nlon [3(L+1)+50] + nlat nlon [4 Ntri + (L+1) + 1] + 8 nlat Ntri."""
+    ntri = (L + 1) * (L + 2) // 2
+    f_grid = nlat * nlon * (4 * ntri + (L + 1) + 1) + nlat * ntri * 8
+    return nlev * nlat * nlon * (3 * (L + 1) + 50) + f_grid
+
+
+def algorithmic_bytes_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON, itemsize=8):
+    """both cubes read once."""
+    return 2 * itemsize * nlev * nlat * nlon
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: oracle port on a bounded latitude sample, process-parallel over time steps
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(seed):
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import numpy as np
+    from oracle import stokes_oracle
+    from oracle.gravtk_standin import plm_holmes
+    from model_harmonics_b200 import testing as syn
+    lat = np.linspace(90.0, -90.0, NLAT)[::SAMPLE_STRIDE]
+    lon = np.arange(NLON) * (360.0 / NLON)
+    GPH, dP, geoid = syn.atmosphere_cube(NLEV, len(lat), NLON, seed=seed)
+    th = np.radians(90.0 - lat)
+    PLM, _ = plm_holmes(LMAX, np.cos(th))          # pre-computed and passed in, as the drivers do
+    w = np.sin(th) * np.radians(360.0 / NLON) * np.radians(180.0 / (NLAT - 1))
+    t0 = time.perf_counter()
+    stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, LMAX=LMAX, ELLIPSOID='WGS84', GEOID=geoid, WEIGHT=w,
+                                        PLM=PLM, LOVE=syn.love_numbers(LMAX), METHOD='BC05')
+    return time.perf_counter() - t0
+
+
+def cpu_arm_step(pool, cores):
+    """
+    One step: every core transforms one latitude-sampled field, all at the same time (so memory
+    contention between cores is in the number).  Each worker times only the operator call (input
+    synthesis and the PLM table are outside, as in the drivers).  Returns (fields/s, wall seconds):
+    process-parallel throughput = sum over workers of (sample fraction / operator time).
+    """
+    nsample = len(range(0, NLAT, SAMPLE_STRIDE))
+    t0 = time.perf_counter()
+    times = pool.map(_cpu_worker, [1234 + i for i in range(cores)], chunksize=1)
+    wall = time.perf_counter() - t0
+    return sum((nsample / float(NLAT)) / t for t in times), wall
+
+
+def cpu_sample_description():
+    nsample = len(range(0, NLAT, SAMPLE_STRIDE))
+    return ('NumPy oracle port of gen_atmosphere_stokes (BC05, PLM precomputed), one field per core, '
+            'latitude rings 0::%d (%d of %d) x %d lon x %d levels, LMAX=%d; fields/s scaled by %d/%d '
+            '(cost is linear in the ring count)' % (SAMPLE_STRIDE, nsample, NLAT, NLON, NLEV, LMAX, nsample, NLAT))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_arm_step(pool, cores)
+        t0 = time.perf_counter()
+        rates = [cpu_arm_step(pool, cores)[0] for _ in range(args.steps)]
+        wall = time.perf_counter() - t0
+    value = sum(rates) / len(rates)
+    line = {
+        'impl': 'reference', 'metric': 'fields_to_stokes_per_second', 'value': value, 'unit': 'fields/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, cores),
+        'cpu_baseline': {'value': value, 'unit': 'fields/s', 'cores': cores, 'kind': 'port',
+                         'sample': cpu_sample_description()},
+        'e2e': {'value': value, 'unit': 'fields/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, cores=None):
+    return {'workload': 'atmosphere_c3', 'operator': 'gen_atmosphere_stokes', 'method': 'BC05',
+            'grid': '%dx%dx%d' % (NLEV, NLAT, NLON), 'lmax': LMAX, 'fields_per_step_per_gpu': args.fields,
+            'input_dtype': 'f64', 'l2_policy': 'inputs exceed L2 (615 MB per field vs 126 MB)',
+            'parallelism': 'time-sharded x%d' % args.gpus}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        self.rows = []
+        self.proc = None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device_index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.rows:
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, cmax = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smmax = cmax
+            if t_begin <= ts <= t_end + 0.1:
+                sm.append(clk)
+                for n, v in zip(names, parts[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+        if not sm:      # region shorter than the sampling period: take everything we saw
+            sm = [float(l.split(',')[1]) for _, l in self.rows if len(l.split(',')) >= 8] or [0.0]
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': smmax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import model_harmonics_b200 as mh
+    from model_harmonics_b200 import _lib, batch, testing as syn
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    L = _lib.lib()
+    T = args.fields
+
+    lon, lat = syn.grid_axes(NLAT, NLON)
+    GPH, dP, geoid = syn.atmosphere_cube(NLEV, NLAT, NLON, seed=1234)
+    LOVE = syn.love_numbers(LMAX)
+    g, d, ge = torch.from_numpy(GPH).to(dev), torch.from_numpy(dP).to(dev), torch.from_numpy(geoid).to(dev)
+    kw = dict(LMAX=LMAX, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE, METHOD='BC05')
+    # this rank's time steps (global index = rank*T + i), SURVEY.md 8(d) scalings
+    scales = np.array([syn.atmosphere_field_scalars(rank * T + i) for i in range(T)])
+
+    def step():
+        clm, slm = mh.atmosphere_stokes_batch(g, d, lon, lat, field_scale=scales, as_numpy=False, **kw)
+        blk = torch.stack([clm, slm], dim=1)
+        if world > 1:
+            blk = batch.gather_coefficients(blk, world * T)      # the only collective: final gather
+        return blk
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    L.mhb200_profile_enable(1)
+    n0 = L.mhb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = int(L.mhb200_launch_count() - n0)
+    import ctypes
+    nrec = ctypes.c_int(0)
+    ring_ms = L.mhb200_profile_mean_ms(ctypes.byref(nrec))
+    L.mhb200_profile_enable(0)
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * T * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the drop-in call with pinned host cubes (H2D + D2H every field)
+    nf = 2
+    host = []
+    for i in range(nf):
+        a, b = syn.atmosphere_field_scalars(rank * T + i)
+        hg = torch.empty((NLEV, NLAT, NLON), dtype=torch.float64, pin_memory=True)
+        hd = torch.empty((NLEV, NLAT, NLON), dtype=torch.float64, pin_memory=True)
+        hg.copy_(torch.from_numpy(GPH) * a)
+        hd.copy_(torch.from_numpy(dP) * b)
+        host.append((hg.numpy(), hd.numpy()))
+    kw_host = dict(LMAX=LMAX, ELLIPSOID='WGS84', GEOID=geoid, LOVE=LOVE, METHOD='BC05')
+
+    def e2e_step():
+        return [mh.gen_atmosphere_stokes(hg, hd, lon, lat, **kw_host) for hg, hd in host]
+
+    Y = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        Y = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        ts = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        e2e_s = float(ts.item())
+    e2e_value = world * nf * e2e_steps / e2e_s
+    h2d = nf * algorithmic_bytes_per_field()
+    d2h = nf * 2 * (LMAX + 1) * (LMAX + 1) * 8
+
+    # parity spot check of what was timed (device-resident field 0 of this rank vs the e2e result)
+    chk = float((out[rank * T if world > 1 else 0, 0].cpu() - torch.from_numpy(Y[0].clm)).abs().max() /
+                np.abs(Y[0].clm).max())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops = algorithmic_flops_per_field() * T
+    achieved = flops / (ring_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ring_kernel_traffic.json')
+    if os.path.isfile(tpath):
+        try:
+            traffic = int(json.load(open(tpath))['dram_bytes_per_field'] * T)
+        except Exception:
+            traffic = None
+    peaks = {}
+    ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(ppath):
+        peaks = json.load(open(ppath))
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    hbm_achieved = algorithmic_bytes_per_field() * T / (ring_ms * 1e-3) / 1e9
+
+    line = {
+        'metric': 'fields_to_stokes_per_second', 'value': value, 'unit': 'fields/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args),
+        'e2e': {'value': e2e_value, 'unit': 'fields/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'fields_per_step': nf, 'steps': e2e_steps, 'call': 'gen_atmosphere_stokes(pinned NumPy fp64 cubes)'},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'tensor', 'kernel': 'stokes_ring_kernel', 'achieved': achieved,
+                     'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS,
+                     'traffic': traffic, 'kernel_ms': ring_ms, 'launches_timed': int(nrec.value),
+                     'flops_per_launch': flops,
+                     'peak_source': 'fp64 DMMA m8n8k4 peak measured on this pool (profiles/r01_fp64_peaks.jsonl); '
+                                    'MEASURED_PEAKS.json holds no fp64 figure; DFMA and DMMA share one pipe',
+                     'hbm': {'achieved': hbm_achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                             'frac': hbm_achieved / hbm_peak,
+                             'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
+        'clocks': clocks,
+        'parity_spot_check_rel_to_max': chk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        with mp.get_context('spawn').Pool(cores) as pool:
+            cpu_value, wall = cpu_arm_step(pool, cores)
+        line['cpu_baseline'] = {'value': cpu_value, 'unit': 'fields/s', 'cores': cores, 'kind': 'port',
+                                'sample': cpu_sample_description(), 'seconds': wall}
+    if world == 1 and not args.no_extra:
+        line['other_workloads'] = other_workloads(mh, syn, torch, L)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_workloads(mh, syn, torch, L):
+    """Device-resident timings of the remaining BASELINE.json configs (median of a few runs)."""
+    import ctypes
+    import numpy as np
+
+    def timeit(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    out = {}
+    LOVE = syn.love_numbers(60)
+    # C1: 12 monthly 1-degree surface pressure fields, LMAX 60
+    lon, lat = syn.grid_axes(181, 360)
+    G, R = syn.surface_geometry(lon, lat)
+    P = syn.pressure_fields(181, 360, 12)
+    Pd, Gd, Rd = [torch.from_numpy(a).cuda() for a in (P, G, R)]
+    ms = timeit(lambda: mh.pressure_stokes_batch(Pd, Gd, Rd, lon, lat, LMAX=60, LOVE=LOVE, as_numpy=False), 10)
+    out['pressure_c1'] = {'config': '12 x 181x360, LMAX=60', 'ms': ms, 'fields_per_s': 12e3 / ms,
+                          'algorithmic_tflops': 12 * 0.500e9 / ms / 1e9}
+    # C2: 1e5 point pressures, LMAX 60
+    pts = syn.point_cloud(100000)
+    dv = [torch.from_numpy(a).cuda() for a in pts]       # P, G, R, lon, lat, AREA all device resident
+    ms = timeit(lambda: mh.point_pressure_batch(dv[0][None], dv[1], dv[2], dv[3], dv[4], AREA=dv[5], LMAX=60,
+                                                LOVE=LOVE, as_numpy=False), 10)
+    out['points_c2'] = {'config': '1e5 points, LMAX=60', 'ms': ms, 'calls_per_s': 1e3 / ms,
+                        'algorithmic_tflops': 2.18e9 / ms / 1e9}
+    # C4: 0.25-degree surface pressure to LMAX 360
+    lon, lat = syn.grid_axes(721, 1440)
+    G, R = syn.surface_geometry(lon, lat)
+    P = syn.pressure_fields(721, 1440, 1)
+    Pd, Gd, Rd = [torch.from_numpy(a).cuda() for a in (P, G, R)]
+    L3 = syn.love_numbers(360)
+    ms = timeit(lambda: mh.pressure_stokes_batch(Pd, Gd, Rd, lon, lat, LMAX=360, LOVE=L3, as_numpy=False), 3, warm=1)
+    out['pressure_c4'] = {'config': '721x1440, LMAX=360', 'ms': ms, 'fields_per_s': 1e3 / ms,
+                          'algorithmic_tflops': 272e9 / ms / 1e9}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--fields', type=int, default=8, help='fields per step per GPU')
+    ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == '__main__':
+    main()

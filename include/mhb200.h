@@ -136,6 +136,13 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
 /* counters for bench.py: kernels launched by this library since load (all threads) */
 uint64_t mhb200_launch_count(void);
 
+/* measurement hook for bench.py: while enabled, every grid/point call brackets its dominant
+ * kernel (stokes_ring_kernel / points_contract_kernel) with CUDA events on the launching
+ * stream; mhb200_profile_mean_ms() waits for them and returns the mean device time (ms) of the
+ * launches recorded since enable (*n = how many), or a negative value if there were none */
+void mhb200_profile_enable(int on);
+double mhb200_profile_mean_ms(int* n);
+
 #ifdef __cplusplus
 }
 #endif

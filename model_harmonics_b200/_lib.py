@@ -26,6 +26,8 @@ PROTOTYPES = {
     'mhb200_device_check': (ctypes.c_int, [ctypes.c_int]),
     'mhb200_last_error': (ctypes.c_char_p, []),
     'mhb200_launch_count': (ctypes.c_uint64, []),
+    'mhb200_profile_enable': (None, [ctypes.c_int]),
+    'mhb200_profile_mean_ms': (ctypes.c_double, [ctypes.POINTER(ctypes.c_int)]),
     'mhb200_plan_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p]),
     'mhb200_plan_destroy': (ctypes.c_int, [_vp]),

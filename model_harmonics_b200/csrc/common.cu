@@ -54,3 +54,50 @@ int mhb200_device_check(int device) {
 }
 
 }  // extern "C"
+
+// ---- optional profiling hook used by bench.py: device time of the dominant kernel of every
+// grid/point call since it was enabled, measured with CUDA events on the launching stream
+namespace mhb {
+constexpr int PROF_RING = 256;
+static bool g_profile = false;
+static cudaEvent_t g_ev[PROF_RING][2];
+static bool g_ev_made = false;
+static int g_ev_count = 0;
+void profile_begin(cudaStream_t st) {
+  if (!g_profile) return;
+  if (!g_ev_made) {
+    for (int i = 0; i < PROF_RING; ++i) {
+      cudaEventCreate(&g_ev[i][0]);
+      cudaEventCreate(&g_ev[i][1]);
+    }
+    g_ev_made = true;
+  }
+  cudaEventRecord(g_ev[g_ev_count % PROF_RING][0], st);
+}
+void profile_end(cudaStream_t st) {
+  if (!g_profile || !g_ev_made) return;
+  cudaEventRecord(g_ev[g_ev_count % PROF_RING][1], st);
+  ++g_ev_count;
+}
+}  // namespace mhb
+
+extern "C" {
+void mhb200_profile_enable(int on) {
+  mhb::g_profile = (on != 0);
+  if (on) mhb::g_ev_count = 0;
+}
+// mean device time (ms) of the launches recorded since enable (at most the last 256); *n = count
+double mhb200_profile_mean_ms(int* n) {
+  const int cnt = mhb::g_ev_count < mhb::PROF_RING ? mhb::g_ev_count : mhb::PROF_RING;
+  if (n) *n = cnt;
+  if (cnt == 0) return -1.0;
+  double sum = 0.0;
+  for (int i = 0; i < cnt; ++i) {
+    if (cudaEventSynchronize(mhb::g_ev[i][1]) != cudaSuccess) return -1.0;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, mhb::g_ev[i][0], mhb::g_ev[i][1]) != cudaSuccess) return -1.0;
+    sum += ms;
+  }
+  return sum / cnt;
+}
+}

@@ -12,6 +12,8 @@ namespace mhb {
 char* err_buf();
 void set_err(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
 
 #define MHB_CUDA(call)                                                              \
   do {                                                                              \

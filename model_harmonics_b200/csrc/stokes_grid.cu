@@ -391,48 +391,67 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 
   for (int kg = 0; kg < nlev; kg += LEV_GROUP) {
     const int ng = min(LEV_GROUP, nlev - kg);
-    // ---- geometry pass: this thread's levels are kg + gpar + 2*i; batches of 4 with the next
-    //      batch's loads in flight (two register sets, loop unrolled by two batches)
+    // ---- geometry pass: this thread's levels are kg + gpar + 2*i.  The raw (z, dp) pair of an
+    //      element and its staged (u0, r) pair are both 16 bytes, so the raw values are copied
+    //      asynchronously (cp.async / LDGSTS) straight into the element's own staging slot -- every
+    //      load of the group is in flight at once and costs no registers -- and overwritten in
+    //      place once computed.  Producer and consumer of a slot are the same thread: only
+    //      cp.async.wait_group is needed, no barrier.
     const int nmine = (ng - gpar + 1) >> 1;
-    const Tin* zq = zp + (size_t)(kg + gpar) * lev_stride;
-    const Tin* dq = dp + (size_t)(kg + gpar) * lev_stride;
-    const size_t step2 = 2 * lev_stride;
-    auto load4 = [&](double(&z)[4], double(&d)[4], int i0) {
+    constexpr int NBATCH = (LEV_GROUP / 2 + GW - 1) / GW;      // batches of GW elements per thread
+    {
+      const Tin* zq = zp + (size_t)(kg + gpar) * lev_stride;
+      const Tin* dq = dp + (size_t)(kg + gpar) * lev_stride;
+      const size_t step2 = 2 * lev_stride;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        z[i] = 0.0;
-        d[i] = 0.0;
-        if (gactive && i0 + i < nmine) {
-          z[i] = ld_as_double(zq + (size_t)(i0 + i) * step2);
-          d[i] = ld_as_double(dq + (size_t)(i0 + i) * step2);
+      for (int b = 0; b < NBATCH; ++b) {
+#pragma unroll
+        for (int i = 0; i < GW; ++i) {
+          const int e = b * GW + i;
+          if (gactive && e < nmine) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&stg[(gpar + 2 * e) * KC + gcol]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(zq + (size_t)e * step2),
+                         "n"(sizeof(Tin)));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + 8), "l"(dq + (size_t)e * step2),
+                         "n"(sizeof(Tin)));
+          }
+        }
+        asm volatile("cp.async.commit_group;");
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NBATCH; ++b) {
+      // groups complete in order: batch b has landed once at most NBATCH-1-b groups are pending
+      if (b == 0) asm volatile("cp.async.wait_group %0;" ::"n"(NBATCH - 1));
+      if (b == 1) asm volatile("cp.async.wait_group %0;" ::"n"(NBATCH > 1 ? NBATCH - 2 : 0));
+      if (b == 2) asm volatile("cp.async.wait_group %0;" ::"n"(NBATCH > 2 ? NBATCH - 3 : 0));
+      if (b == 3) asm volatile("cp.async.wait_group %0;" ::"n"(NBATCH > 3 ? NBATCH - 4 : 0));
+      if (b >= 4) asm volatile("cp.async.wait_group 0;");
+      if (b * GW < nmine) {
+        double zs[GW], ds[GW], u0[GW], r[GW];
+#pragma unroll
+        for (int i = 0; i < GW; ++i) {
+          const int e = b * GW + i;
+          zs[i] = 0.0;
+          ds[i] = 0.0;
+          if (gactive && e < nmine) {
+            const Tin* raw = reinterpret_cast<const Tin*>(&stg[(gpar + 2 * e) * KC + gcol]);
+            zs[i] = sg * (double)raw[0];
+            ds[i] = sp * (double)raw[8 / sizeof(Tin)];
+          }
+        }
+        level_elements<MODE>(zs, ds, cg, u0, r);
+#pragma unroll
+        for (int i = 0; i < GW; ++i) {
+          const int e = b * GW + i;
+          if (lb > 0) u0[i] *= ipow(r[i], lb * LBLK);
+          if (!gactive) {
+            u0[i] = 0.0;
+            r[i] = 1.0;
+          }
+          if (e < nmine) stg[(gpar + 2 * e) * KC + gcol] = make_double2(u0[i], r[i]);
         }
       }
-    };
-    auto compute4 = [&](const double(&z)[4], const double(&d)[4], int i0) {
-      double zs[4], ds[4], u0[4], r[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        zs[i] = sg * z[i];
-        ds[i] = sp * d[i];
-      }
-      level_elements<MODE>(zs, ds, cg, u0, r);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (lb > 0) u0[i] *= ipow(r[i], lb * LBLK);
-        if (!gactive) {
-          u0[i] = 0.0;
-          r[i] = 1.0;
-        }
-        if (i0 + i < nmine) stg[(gpar + 2 * (i0 + i)) * KC + gcol] = make_double2(u0[i], r[i]);
-      }
-    };
-    double zA[4], dA[4], zB[4], dB[4];
-    load4(zA, dA, 0);
-    for (int i0 = 0; i0 < nmine; i0 += 8) {
-      load4(zB, dB, i0 + 4);
-      compute4(zA, dA, i0);
-      load4(zA, dA, i0 + 8);
-      compute4(zB, dB, i0 + 4);
     }
     __syncthreads();
     // ---- accumulate pass
@@ -851,7 +870,9 @@ template <int MODE, typename Tin, int NTH>
 int launch_ring_shape(const GridParams& gp, int ncta, cudaStream_t st) {
   auto kern = stokes_ring_kernel<MODE, Tin, NTH>;
   MHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape<NTH>::SMEM));
+  profile_begin(st);
   kern<<<ncta, NTH, Shape<NTH>::SMEM, st>>>(gp);
+  profile_end(st);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());
   return MHB200_OK;

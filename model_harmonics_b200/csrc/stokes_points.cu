@@ -215,26 +215,38 @@ __global__ void __launch_bounds__(PT_NT, 1) points_contract_kernel(const PointPa
   }
 }
 
-// grid (lmax+1, nbatch): out = dfactor[l] * sum over CTA partials in fixed order
-__global__ void points_reduce_kernel(const PointParams q, const __grid_constant__ DegreeFactors dfs) {
+// grid (lmax+1, nbatch), 256 threads: out = dfactor[l] * sum over CTA partials.  Four interleaved
+// partial sums per (l, m) keep independent loads in flight; they are combined in a fixed order.
+__global__ void __launch_bounds__(256) points_reduce_kernel(const PointParams q,
+                                                            const __grid_constant__ DegreeFactors dfs) {
+  __shared__ double part[2][4][64];
   const int l = blockIdx.x, t = blockIdx.y;
   const int ncol = q.mmax + 1;
   const size_t plane = (size_t)(q.lmax + 1) * ncol;
   const double df = (dfs.dev != nullptr) ? dfs.dev[l] : dfs.v[l];
-  for (int m = threadIdx.x; m < ncol; m += blockDim.x) {
+  const int ml = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (int m0 = 0; m0 < ncol; m0 += 64) {
+    const int m = m0 + ml;
     double c = 0.0, s = 0.0;
-    if (m <= l) {
-      for (int k = 0; k < q.ncta_p; ++k) {
+    if (m <= l && m < ncol) {
+#pragma unroll 4
+      for (int k = grp; k < q.ncta_p; k += 4) {
         const double* slot = q.slots + ((size_t)k * q.nbatch + t) * 2 * plane;
         c += slot[(size_t)l * ncol + m];
         s += slot[plane + (size_t)l * ncol + m];
       }
-      c *= df;
-      s *= df;
     }
-    const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
-    q.clm[o] = c;
-    q.slm[o] = s;
+    part[0][grp][ml] = c;
+    part[1][grp][ml] = s;
+    __syncthreads();
+    if (grp == 0 && m < ncol) {
+      const double cc = ((part[0][0][ml] + part[0][1][ml]) + (part[0][2][ml] + part[0][3][ml])) * df;
+      const double ss = ((part[1][0][ml] + part[1][1][ml]) + (part[1][2][ml] + part[1][3][ml])) * df;
+      const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
+      q.clm[o] = (m <= l) ? cc : 0.0;
+      q.slm[o] = (m <= l) ? ss : 0.0;
+    }
+    __syncthreads();
   }
 }
 
@@ -428,13 +440,15 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
     }
     MHB_CUDA(cudaFuncSetAttribute(points_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(y.ncta_p, y.n_mtiles, nbatch);
+    profile_begin(st);
     points_contract_kernel<<<grid, PT_NT, smem, st>>>(q);
+    profile_end(st);
     g_launches.fetch_add(1);
     MHB_CUDA(cudaGetLastError());
   }
   {
     dim3 grid(lmax + 1, nbatch);
-    points_reduce_kernel<<<grid, 64, 0, st>>>(q, dfs);
+    points_reduce_kernel<<<grid, 256, 0, st>>>(q, dfs);
     g_launches.fetch_add(1);
     MHB_CUDA(cudaGetLastError());
   }

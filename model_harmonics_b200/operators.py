@@ -354,9 +354,15 @@ def _point_operand(a, device, npts, name):
 def _points_prepare(lon, lat, AREA, LMAX, MMAX, LOVE, device):
     if MMAX is None:                                                 # :107-108 (MMAX=0 stays 0)
         MMAX = np.copy(LMAX)
-    phi = np.radians(_flat(lon) if not isinstance(lon, torch.Tensor) else lon.cpu().numpy().flatten())   # :111-113
-    theta = np.radians(90.0 - (_flat(lat) if not isinstance(lat, torch.Tensor) else lat.cpu().numpy().flatten()))
-    npts = len(phi)
+    if isinstance(lon, torch.Tensor) and isinstance(lat, torch.Tensor):
+        # device-resident coordinates: np.radians(x) is the single multiply x*(pi/180), formed here
+        # in fp64 on the device with the same constant
+        phi_t = _to_device(lon, device).reshape(-1) * (np.pi / 180.0)               # :111-113
+        theta_t = (90.0 - _to_device(lat, device).reshape(-1)) * (np.pi / 180.0)
+    else:
+        phi_t = _to_device(np.radians(_flat(lon)), device)
+        theta_t = _to_device(np.radians(90.0 - _flat(lat)), device)
+    npts = phi_t.numel()
     factors = _compat.units(lmax=LMAX).spatial(*LOVE)                # :116-122
     rad_e = factors.rad_e / 100.0
     dfactor = 4.0 * np.pi * factors.mmwe / (1.0 + 2.0 * factors.l)
@@ -364,9 +370,7 @@ def _points_prepare(lon, lat, AREA, LMAX, MMAX, LOVE, device):
     area_t, _ = _point_operand(area, device, npts, 'AREA')
     if area_t.numel() != npts:
         area_t = area_t.expand(npts).contiguous()
-    phi_t = _to_device(phi, device)
-    theta_t = _to_device(theta, device)
-    return MMAX, npts, rad_e, dfactor, phi_t, theta_t, area_t
+    return MMAX, npts, rad_e, dfactor, phi_t.contiguous(), theta_t.contiguous(), area_t
 
 
 def gen_point_pressure(P, G, R, lon, lat, AREA=None, LMAX=60, MMAX=None, LOVE=None):
