@@ -13,10 +13,10 @@
 //      Pdisc_l = (P_{l-1}(alpha) - P_{l+1}(alpha))/2 is a cancellation-prone 3-term recursion
 //      (error amplified by ~1/(1-alpha) ~ npts/2), so it is evaluated in EXACTLY the
 //      reference's operation order with round-to-nearest intrinsics and no FMA contraction.
-//  (2) points_contract_kernel: scatter-reduce.  A lane group of 8 lanes owns one pair of
+//  (2) points_contract_kernel: scatter-reduce.  A lane group of 4 lanes owns one pair of
 //      orders (m, mtop-m) -- pairing makes every lane walk the same number of degrees -- and
 //      each lane carries 8 points at a time through the Holmes-Featherstone recursion in
-//      registers (Plm normalisation identical to legendre(NORMALIZE=True)); the 8 lanes are
+//      registers (Plm normalisation identical to legendre(NORMALIZE=True)); the 4 lanes are
 //      combined with warp shuffles and added to accumulators private to the lane group in
 //      shared memory.  Per-CTA partials go to slots that a final kernel reduces in fixed order
 //      (deterministic; no fp64 atomics).
@@ -31,11 +31,11 @@
 
 namespace mhb {
 
-constexpr int PT_NT = 256;       // threads per CTA
+constexpr int PT_NT = 128;       // threads per CTA (two CTAs per SM)
 constexpr int PT_PER_LANE = 8;   // points carried per lane
-constexpr int PT_GROUPS = 8;     // lanes per order pair
-constexpr int PT_BATCH = PT_PER_LANE * PT_GROUPS;   // 64 points per pass
-constexpr int PT_PAIRS = 32;     // order pairs per CTA (4 per warp)
+constexpr int PT_GROUPS = 4;     // lanes per order pair
+constexpr int PT_BATCH = PT_PER_LANE * PT_GROUPS;   // 32 points per pass
+constexpr int PT_PAIRS = 32;     // order pairs per CTA (8 per warp)
 constexpr int PT_MTILE = 2 * PT_PAIRS;
 
 struct PointParams {
@@ -92,13 +92,13 @@ __global__ void points_weights_kernel(const PointParams q) {
 }
 
 // grid: (ncta_p, n_mtiles, nbatch)
-__global__ void __launch_bounds__(PT_NT, 1) points_contract_kernel(const PointParams q) {
+__global__ void __launch_bounds__(PT_NT, 2) points_contract_kernel(const PointParams q) {
   extern __shared__ double acc_s[];   // [PT_PAIRS][2][pitch]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane & (PT_GROUPS - 1);
-  const int pair = warp * 4 + (lane >> 3);
+  const int pair = warp * (32 / PT_GROUPS) + lane / PT_GROUPS;
   // lane groups of one warp walk different degree ranges: shuffles name only the group's lanes
-  const unsigned gmask = 0xFFu << (lane & 24);
+  const unsigned gmask = ((1u << PT_GROUPS) - 1u) << (lane & ~(PT_GROUPS - 1));
   const int t = blockIdx.z;
   const int L = q.lmax;
   // orders of this CTA's tile and of this lane group's pair
@@ -134,12 +134,14 @@ __global__ void __launch_bounds__(PT_NT, 1) points_contract_kernel(const PointPa
       for (int which = 0; which < 2; ++which) {
         if (which == 1 && !has_b) break;
         const int m = which ? mb : ma;
-        double cm[PT_PER_LANE], sm[PT_PER_LANE], p1[PT_PER_LANE], p2[PT_PER_LANE], rs[PT_PER_LANE];
+        // per (point, order): e^{i m phi} (:186-188) with the u^m/1e-280 rescale of the scaled
+        // Holmes-Featherstone column folded in, and the two recursion seeds
+        double cm[PT_PER_LANE], sm[PT_PER_LANE], p1[PT_PER_LANE], p2[PT_PER_LANE];
         const double pmm = q.pmm[m], sqm = q.sq[m];
 #pragma unroll
         for (int i = 0; i < PT_PER_LANE; ++i) {
-          sincos((double)m * ph[i], &sm[i], &cm[i]);     // e^{i m phi}, :186-188
-          // u^m / 1e-280 by binary powering
+          double sv, cv;
+          sincos((double)m * ph[i], &sv, &cv);
           double r = (m == 0) ? 1.0 : 1.0e280, bb = u[i];
           int e = m;
           while (e) {
@@ -147,50 +149,70 @@ __global__ void __launch_bounds__(PT_NT, 1) points_contract_kernel(const PointPa
             bb *= bb;
             e >>= 1;
           }
-          rs[i] = r;
-          p2[i] = pmm;                                         // degree m
-          p1[i] = __dmul_rn(__dmul_rn(x[i], sqm), pmm);        // degree m+1
+          cm[i] = r * cv;
+          sm[i] = r * sv;
+          p2[i] = pmm;                      // degree m
+          p1[i] = (x[i] * sqm) * pmm;       // degree m+1
         }
-        const double* f1 = q.f1 + m;
-        const double* f2 = q.f2 + m;
-        for (int l = m; l <= L; ++l, ++step) {
-          // Plm for the 8 points at degree l
-          double pl[PT_PER_LANE];
-          if (l == m) {
-#pragma unroll
-            for (int i = 0; i < PT_PER_LANE; ++i) pl[i] = p2[i];
-          } else if (l == m + 1) {
-#pragma unroll
-            for (int i = 0; i < PT_PER_LANE; ++i) pl[i] = p1[i];
-          } else {
-            const double a = __ldg(f1 + (size_t)l * q.Mpad), bq = __ldg(f2 + (size_t)l * q.Mpad);
-#pragma unroll
-            for (int i = 0; i < PT_PER_LANE; ++i) {
-              pl[i] = __dsub_rn(__dmul_rn(__dmul_rn(x[i], a), p1[i]), __dmul_rn(bq, p2[i]));
-              p2[i] = p1[i];
-              p1[i] = pl[i];
-            }
-          }
-          const double* Wl = Wt + (size_t)l * q.npad + pbase;
-          const double4 w0 = *reinterpret_cast<const double4*>(Wl);
-          const double4 w1 = *reinterpret_cast<const double4*>(Wl + 4);
+        // W rows are fetched one degree ahead
+        const double* Wl = Wt + (size_t)m * q.npad + pbase;
+        double4 wa = *reinterpret_cast<const double4*>(Wl);
+        double4 wb = *reinterpret_cast<const double4*>(Wl + 4);
+        auto emit = [&](const double(&pl)[PT_PER_LANE], const double4& w0, const double4& w1) {
           const double w[PT_PER_LANE] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-          double c = 0.0, s = 0.0;
+          double c = 0.0, s2 = 0.0;
 #pragma unroll
           for (int i = 0; i < PT_PER_LANE; ++i) {
-            const double tv = (pl[i] * rs[i]) * w[i];
+            const double tv = pl[i] * w[i];
             c = fma(tv, cm[i], c);
-            s = fma(tv, sm[i], s);
+            s2 = fma(tv, sm[i], s2);
           }
-          // combine the 8 lanes of the group (fixed butterfly order)
+          // combine the lanes of the group (fixed butterfly order)
 #pragma unroll
-          for (int off = 4; off >= 1; off >>= 1) {
+          for (int off = PT_GROUPS / 2; off >= 1; off >>= 1) {
             c += __shfl_xor_sync(gmask, c, off);
-            s += __shfl_xor_sync(gmask, s, off);
+            s2 += __shfl_xor_sync(gmask, s2, off);
           }
           if (g == 0) {
             acc_c[step] += c;
-            acc_sn[step] += s;
+            acc_sn[step] += s2;
+          }
+          ++step;
+        };
+        auto next_w = [&](int l, double4& w0, double4& w1) {
+          const int ln = min(l, L);
+          const double* Wn = Wt + (size_t)ln * q.npad + pbase;
+          w0 = *reinterpret_cast<const double4*>(Wn);
+          w1 = *reinterpret_cast<const double4*>(Wn + 4);
+        };
+        // degree m
+        double4 wc = wa, wd = wb;
+        next_w(m + 1, wa, wb);
+        emit(p2, wc, wd);
+        if (m + 1 <= L) {
+          // degree m+1
+          wc = wa;
+          wd = wb;
+          next_w(m + 2, wa, wb);
+          const double* f1 = q.f1 + m;
+          const double* f2 = q.f2 + m;
+          double fa = __ldg(f1 + (size_t)min(m + 2, L) * q.Mpad), fb = __ldg(f2 + (size_t)min(m + 2, L) * q.Mpad);
+          emit(p1, wc, wd);
+          for (int l = m + 2; l <= L; ++l) {
+            const double a = fa, bq = fb;
+            wc = wa;
+            wd = wb;
+            next_w(l + 1, wa, wb);
+            fa = __ldg(f1 + (size_t)min(l + 1, L) * q.Mpad);
+            fb = __ldg(f2 + (size_t)min(l + 1, L) * q.Mpad);
+            double pl[PT_PER_LANE];
+#pragma unroll
+            for (int i = 0; i < PT_PER_LANE; ++i) {
+              pl[i] = fma(x[i] * a, p1[i], -(bq * p2[i]));
+              p2[i] = p1[i];
+              p1[i] = pl[i];
+            }
+            emit(pl, wc, wd);
           }
         }
       }
@@ -268,7 +290,7 @@ PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num
   y.Mpad = (mmax + 64) / 64 * 64;
   y.n_mtiles = (mmax + PT_MTILE) / PT_MTILE;
   const long long nbatches = y.npad / PT_BATCH;
-  const long long want = std::max<long long>(1, (long long)num_sms / (y.n_mtiles * (long long)nbatch));
+  const long long want = std::max<long long>(1, 2LL * num_sms / (y.n_mtiles * (long long)nbatch));
   y.ncta_p = (int)std::min<long long>(nbatches, std::max<long long>(want, 1));
   y.batches_per_cta = (int)((nbatches + y.ncta_p - 1) / y.ncta_p);
   y.ncta_p = (int)((nbatches + y.batches_per_cta - 1) / y.batches_per_cta);
