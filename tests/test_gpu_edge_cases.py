@@ -1,0 +1,149 @@
+"""
+GPU parity at the awkward sizes: tile and chunk boundaries, multi-group level loops, tiny grids,
+single points, high degree; plus oracle-free properties at the BASELINE sizes.
+"""
+import numpy as np
+import pytest
+
+from parity import TOL, rel_to_max, assert_structure
+
+pytestmark = pytest.mark.gpu
+
+
+def _mh():
+    import model_harmonics_b200 as mh
+    return mh
+
+
+def _syn():
+    from model_harmonics_b200 import testing as syn
+    return syn
+
+
+@pytest.mark.parametrize('nlat,nlon,L,M', [
+    (2, 4, 0, None), (3, 7, 1, None), (5, 9, 2, 1), (19, 37, 63, None), (19, 36, 64, None),
+    (21, 40, 65, 63), (17, 33, 70, 64), (13, 130, 20, None), (11, 257, 12, 5), (9, 129, 130, 3),
+])
+def test_pressure_boundary_sizes(nlat, nlon, L, M):
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    rng = np.random.default_rng(nlat * 1000 + nlon)
+    lat = np.linspace(88.0, -88.0, nlat)
+    lon = np.arange(nlon) * (360.0 / nlon)
+    P = 500.0 * rng.standard_normal((nlat, nlon))
+    G = 9.8 + 0.01 * rng.standard_normal((nlat, nlon))
+    R = 6.371e6 + 2.0e3 * rng.standard_normal((nlat, nlon))
+    kw = dict(LMAX=L, MMAX=M, LOVE=syn.love_numbers(L))
+    A = mh.gen_pressure_stokes(P, G, R, lon, lat, **kw)
+    B = stokes_oracle.gen_pressure_stokes(P, G, R, lon, lat, **kw)
+    assert_structure(A.clm, A.slm, int(B.lmax), int(B.mmax))
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+
+
+@pytest.mark.parametrize('nlev,nlat,nlon,L,M,method', [
+    (1, 7, 12, 5, None, 'BC05'), (2, 9, 16, 8, 3, 'SW02'), (41, 9, 20, 10, None, 'BC05'),
+    (80, 7, 16, 6, None, 'BC05'), (81, 7, 16, 6, None, 'SW02'), (5, 11, 70, 66, None, 'BC05'),
+    (3, 9, 131, 70, 20, 'SW02'),
+])
+def test_atmosphere_boundary_sizes(nlev, nlat, nlon, L, M, method):
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    lat = np.linspace(90.0, -90.0, nlat)
+    lon = np.arange(nlon) * (360.0 / nlon)
+    GPH, dP, geoid = syn.atmosphere_cube(nlev, nlat, nlon, seed=nlev + nlon)
+    kw = dict(LMAX=L, MMAX=M, ELLIPSOID='WGS84', GEOID=geoid, LOVE=syn.love_numbers(L), METHOD=method)
+    A = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    B = stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    assert_structure(A.clm, A.slm, int(B.lmax), int(B.mmax))
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+    # scalar geoid broadcasts (reference: N + GEOID)
+    kw['GEOID'] = 12.5
+    A = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    B = stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+
+
+@pytest.mark.parametrize('n,L,M', [(1, 4, None), (31, 0, None), (33, 1, None), (257, 70, None), (100, 100, 64),
+                                    (64, 12, 0)])
+def test_points_boundary_sizes(n, L, M):
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    P, G, R, lon, lat, AREA = syn.point_cloud(n, seed=n + L, pole_points=(n >= 8))
+    kw = dict(AREA=AREA, LMAX=L, MMAX=M, LOVE=syn.love_numbers(L))
+    A = mh.gen_point_pressure(P, G, R, lon, lat, **kw)
+    B = stokes_oracle.gen_point_pressure(P, G, R, lon, lat, **kw)
+    assert A.clm.shape == B.clm.shape
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+
+
+def test_pressure_lmax360_against_oracle():
+    """High degree (21 tiles, FULL + DIAG paths, deep Legendre recursion incl. polar underflow)."""
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    lon, lat = syn.grid_axes(91, 180)
+    G, R = syn.surface_geometry(lon, lat, seed=4)
+    P = syn.pressure_fields(91, 180, 1, seed=4)[0]
+    kw = dict(LMAX=360, LOVE=syn.love_numbers(360))
+    A = mh.gen_pressure_stokes(P, G, R, lon, lat, **kw)
+    B = stokes_oracle.gen_pressure_stokes(P, G, R, lon, lat, **kw)
+    assert_structure(A.clm, A.slm, 360, 360)
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+
+
+def test_full_size_properties_pressure_c4():
+    """0.25 degree, LMAX=360, no oracle: linearity, longitude-shift phase rotation, zonal field."""
+    import torch
+    mh, syn = _mh(), _syn()
+    nlat, nlon, L = 721, 1440, 360
+    lon, lat = syn.grid_axes(nlat, nlon)
+    LOVE = syn.love_numbers(L)
+    rng = np.random.default_rng(77)
+    P1 = torch.from_numpy(500.0 * rng.standard_normal((nlat, nlon))).cuda()
+    P2 = torch.from_numpy(500.0 * rng.standard_normal((nlat, nlon))).cuda()
+    k = 37                                           # shift by 37 cells in longitude
+    zonal = torch.from_numpy(np.repeat(300.0 * rng.standard_normal((nlat, 1)), nlon, axis=1)).cuda()
+    batch = torch.stack([P1, P2, 2.0 * P1 - 0.5 * P2, torch.roll(P1, k, dims=1), zonal])
+    # constant G and a radius that depends on latitude only keep the shift property exact
+    Rlat = torch.from_numpy(6.371e6 + 1.0e4 * np.cos(np.radians(lat))[:, None] * np.ones((1, nlon))).cuda()
+    clm, slm = mh.pressure_stokes_batch(batch, 9.81, Rlat, lon, lat, LMAX=L, LOVE=LOVE)
+    scale = np.abs(clm[0]).max()
+    # linearity
+    assert np.abs(2.0 * clm[0] - 0.5 * clm[1] - clm[2]).max() <= 1e-12 * scale
+    assert np.abs(2.0 * slm[0] - 0.5 * slm[1] - slm[2]).max() <= 1e-12 * scale
+    # field shifted east by k cells: (C + iS)_m -> (C + iS)_m * exp(i m k dphi)
+    ang = np.arange(L + 1) * (k * 2.0 * np.pi / nlon)
+    z = (clm[0] + 1j * slm[0]) * np.exp(1j * ang)[None, :]
+    assert np.abs(z.real - clm[3]).max() <= 1e-11 * scale
+    assert np.abs(z.imag - slm[3]).max() <= 1e-11 * scale
+    # zonal field: only order 0
+    zs = np.abs(clm[4][:, 0]).max()
+    assert np.abs(clm[4][:, 1:]).max() <= 1e-12 * zs and np.abs(slm[4]).max() <= 1e-12 * zs
+    for t in range(5):
+        assert_structure(clm[t], slm[t], L, L)
+
+
+def test_full_size_properties_atmosphere_c3():
+    """ERA5-shaped cube: dP linearity and sign, batch scale factors, against a latitude sub-sampled oracle run."""
+    import torch
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    nlev, nlat, nlon, L = 37, 721, 1440, 60
+    lon, lat = syn.grid_axes(nlat, nlon)
+    GPH, dP, geoid = syn.atmosphere_cube(nlev, nlat, nlon, seed=1234)
+    LOVE = syn.love_numbers(L)
+    g, d = torch.from_numpy(GPH).cuda(), torch.from_numpy(dP).cuda()
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=torch.from_numpy(geoid).cuda(), LOVE=LOVE)
+    sc = np.array([[1.0, 1.0], [1.0, -2.0], [1.0, 0.25]])
+    clm, slm = mh.atmosphere_stokes_batch(g, d, lon, lat, field_scale=sc, **kw)
+    scale = np.abs(clm[0]).max()
+    # the transform is linear in dP for fixed GPH
+    assert np.abs(clm[1] + 2.0 * clm[0]).max() <= 1e-13 * scale
+    assert np.abs(slm[2] - 0.25 * slm[0]).max() <= 1e-13 * scale
+    # rings are additive: rings 0::8 with explicit weights, CUDA vs oracle (a few seconds of CPU)
+    sub = slice(0, nlat, 8)
+    th = np.radians(90.0 - lat[sub])
+    w = np.sin(th) * np.radians(0.25) * np.radians(0.25)
+    kw2 = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=geoid[sub], WEIGHT=w, LOVE=LOVE)
+    A = mh.gen_atmosphere_stokes(GPH[:, sub], dP[:, sub], lon, lat[sub], **kw2)
+    B = stokes_oracle.gen_atmosphere_stokes(GPH[:, sub], dP[:, sub], lon, lat[sub], **kw2)
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
