@@ -555,53 +555,56 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
       // table: one coalesced 256-byte load per fragment, prefetched three k-steps ahead in a
       // register ring), B fragments from shared memory one k-step ahead
       const double* Ablk = p.trig + ((size_t)(seg.mb * p.nks_total + chunk * nksc) * 16) * 32 + lane;
+      // loads take a clamped k-step index, so they are unconditional (straight-line code the
+      // compiler can hoist); a clamped load past the end fetches a valid fragment that is never used
+      const int klast = nksc - 1;
       auto load_a = [&](double(&a)[NA], int k) {
-        if (k < nksc) {
-          const double* ap = Ablk + (size_t)k * 512;
-          a[0] = __ldg(ap + (gA * 2) * 32);
-          a[1] = __ldg(ap + (gA * 2 + 1) * 32);
-          if (DIAG) {
-            a[2] = __ldg(ap + (gB * 2) * 32);
-            a[3] = __ldg(ap + (gB * 2 + 1) * 32);
-          }
+        const double* ap = Ablk + (size_t)min(k, klast) * 512;
+        a[0] = __ldg(ap + (gA * 2) * 32);
+        a[1] = __ldg(ap + (gA * 2 + 1) * 32);
+        if (DIAG) {
+          a[2] = __ldg(ap + (gB * 2) * 32);
+          a[3] = __ldg(ap + (gB * 2 + 1) * 32);
         }
       };
       const int brot = lane >> 2, bcol = lane & 3;
       auto load_b = [&](double(&b)[NP], int k) {
-        if (k < nksc) {
-          const double* Bk = Bs + k * 256 + (((brot + k) & 7) << 2) + bcol;
+        const int kc2 = min(k, klast);
+        const double* Bk = Bs + kc2 * 256 + (((brot + kc2) & 7) << 2) + bcol;
 #pragma unroll
-          for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
+        for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
+      };
+      auto mma_step = [&](const double(&c)[NA], const double(&bb)[NP]) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const bool first = (!DIAG) || (j < nA);
+          dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], bb[j]);
+          dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], bb[j]);
         }
       };
       double a[4][NA], b[2][NP];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < NA; ++j) a[i][j] = 0.0;
-#pragma unroll
-      for (int j = 0; j < NP; ++j) b[0][j] = b[1][j] = 0.0;
       const int k0 = sub;
 #pragma unroll
       for (int i = 0; i < 3; ++i) load_a(a[i], k0 + i * KSTRIDE);
       load_b(b[0], k0);
-      // 4-deep trig ring / 2-deep B ring, fully unrolled: no rotation copies
-      for (int ks = k0; ks < nksc; ks += 4 * KSTRIDE) {
+      // 4-deep trig ring / 2-deep B ring, fully unrolled: no rotation copies.  Main loop: groups
+      // of four k-steps with no guards; tail: the remaining (< 4) k-steps.
+      int ks = k0;
+      for (; ks + 3 * KSTRIDE < nksc; ks += 4 * KSTRIDE) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int k = ks + u * KSTRIDE;
-          if (k < nksc) {
-            load_a(a[(u + 3) & 3], k + 3 * KSTRIDE);
-            load_b(b[(u + 1) & 1], k + KSTRIDE);
-            const double(&c)[NA] = a[u];
-            const double(&bb)[NP] = b[u & 1];
+          load_a(a[(u + 3) & 3], k + 3 * KSTRIDE);
+          load_b(b[(u + 1) & 1], k + KSTRIDE);
+          mma_step(a[u], b[u & 1]);
+        }
+      }
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {
-              const bool first = (!DIAG) || (j < nA);
-              dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], bb[j]);
-              dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], bb[j]);
-            }
-          }
+      for (int u = 0; u < 3; ++u) {
+        const int k = ks + u * KSTRIDE;
+        if (k < nksc) {
+          load_b(b[(u + 1) & 1], k + KSTRIDE);
+          mma_step(a[u], b[u & 1]);
         }
       }
       __syncthreads();
