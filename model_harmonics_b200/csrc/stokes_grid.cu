@@ -68,6 +68,8 @@ struct GridParams {
   int nlat, nlon, lmax, mmax, Mpad, kc, nchunks, nks_total;
   const double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
   const double* plm_table;
+  const double* ckpt;          // Legendre restart states [nlat][nlb][Mpad][2] (nlb > 1), else null
+  int nlb;
   const Segment* segs;
   const int* cta_seg_begin;
   double* slots;
@@ -131,14 +133,26 @@ __device__ __forceinline__ void legendre_ring(const GridParams& p, int h, int lb
     const int l = lbase + j;
     if (l < m || l > p.lmax) row[j] = 0.0;
   }
-  double p2 = p.pmm[m];  // degree m (sectoral), scaled
-  if (m >= lbase) row[m - lbase] = __dmul_rn(__dmul_rn(p2, rs), wh);
-  if (m + 1 > lend) return;
-  double p1 = __dmul_rn(__dmul_rn(x, p.sq[m]), p2);  // degree m+1
-  if (m + 1 >= lbase) row[m + 1 - lbase] = __dmul_rn(__dmul_rn(p1, rs), wh);
   const double* f1 = p.f1 + m;
   const double* f2 = p.f2 + m;
-  for (int l0 = m + 2; l0 <= lend; l0 += 8) {
+  double p2, p1;
+  int lstart;
+  if (p.ckpt != nullptr && lb > 0 && m <= lbase - 2) {
+    // restart from the states stored at degrees lbase-2, lbase-1 (same arithmetic as the full
+    // chain, so the values are bit-identical): the recursion never walks more than ~65 degrees
+    const double* ck = p.ckpt + (((size_t)h * p.nlb + lb) * p.Mpad + m) * 2;
+    p2 = ck[0];
+    p1 = ck[1];
+    lstart = lbase;
+  } else {
+    p2 = p.pmm[m];  // degree m (sectoral), scaled
+    if (m >= lbase) row[m - lbase] = __dmul_rn(__dmul_rn(p2, rs), wh);
+    if (m + 1 > lend) return;
+    p1 = __dmul_rn(__dmul_rn(x, p.sq[m]), p2);  // degree m+1
+    if (m + 1 >= lbase) row[m + 1 - lbase] = __dmul_rn(__dmul_rn(p1, rs), wh);
+    lstart = m + 2;
+  }
+  for (int l0 = lstart; l0 <= lend; l0 += 8) {
     // multipliers for 8 degrees are fetched together so their L2 latency overlaps
     double a[8], b[8];
 #pragma unroll
@@ -160,6 +174,36 @@ __device__ __forceinline__ void legendre_ring(const GridParams& p, int h, int lb
   }
 }
 
+// One-off (per plan) kernel: runs every (ring, order) column once and stores the recursion state
+// at each degree-block boundary (a 1/32 sample of the table the reference materialises).
+__global__ void legendre_checkpoint_kernel(int nlat, int lmax, int mmax, int Mpad, int nlb, const double* x,
+                                           const double* f1, const double* f2, const double* pmm,
+                                           const double* sq, double* ckpt) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  if (m > mmax || h >= nlat) return;
+  const double xv = x[h];
+  double p2 = pmm[m];
+  double p1 = __dmul_rn(__dmul_rn(xv, sq[m]), p2);
+  // (p2, p1) = (P_{l-1}, P_l) after degree l; a checkpoint is wanted at l = 64*lb - 1
+  for (int l = m + 1; l <= lmax; ++l) {
+    if (l > m + 1) {
+      const double pl = __dsub_rn(__dmul_rn(__dmul_rn(xv, f1[(size_t)l * Mpad + m]), p1),
+                                  __dmul_rn(f2[(size_t)l * Mpad + m], p2));
+      p2 = p1;
+      p1 = pl;
+    }
+    if (((l + 1) % LBLK) == 0) {
+      const int lb = (l + 1) / LBLK;
+      if (lb < nlb && m <= lb * LBLK - 2) {
+        double* ck = ckpt + (((size_t)h * nlb + lb) * Mpad + m) * 2;
+        ck[0] = p2;
+        ck[1] = p1;
+      }
+    }
+  }
+}
+
 // B-fragment slot of element (l_local, column) inside the chunk buffer.  Fragment-major:
 // [kstep][degree-tile][32 slots]; the row is rotated by kstep so that both the producer's
 // stores (16 columns x fixed degree per half-warp) and the consumer's fragment loads are
@@ -173,22 +217,36 @@ __device__ __forceinline__ int bs_index(int l_local, int col) {
 // Produce phase, pressure:  B[p,l] = (P/G) * (R/rad_e)^(l+2)   (gen_pressure_stokes.py:200)
 // A column is shared by two threads (warps w and w + NW/2): each handles 32 of the 64 degrees.
 // ---------------------------------------------------------------------------------------
+// values of one grid cell for the pressure produce phase, loaded one chunk ahead
+struct PressureCell {
+  double P, G, R;
+};
 template <int NTH>
-__device__ __forceinline__ void produce_pressure(const GridParams& p, int t, int h, int lb, int chunk,
-                                                 double* Bs) {
+__device__ __forceinline__ PressureCell load_pressure_cell(const GridParams& p, int t, int h, int chunk) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NWH = NTH / 64;
+  const int col = (warp % NWH) * 32 + lane;
+  const int pcol = chunk * p.kc + col;
+  PressureCell c;
+  c.P = 0.0;
+  c.G = 1.0;
+  c.R = p.rad_e;
+  if (col < p.kc && pcol < p.nlon && h < p.nlat) {
+    c.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pcol * p.Ps[2]);
+    c.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pcol * p.Gs[2]);
+    c.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pcol * p.Rs[2]);
+  }
+  return c;
+}
+
+template <int NTH>
+__device__ __forceinline__ void produce_pressure(const GridParams& p, const PressureCell& cell, int lb, double* Bs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWH = NTH / 64;
   const int half = warp / NWH, col = (warp % NWH) * 32 + lane;
   if (col >= p.kc) return;
-  const int pcol = chunk * p.kc + col;
-  double f = 0.0, r = 1.0;
-  if (pcol < p.nlon) {
-    const double Pv = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pcol * p.Ps[2]);
-    const double Gv = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pcol * p.Gs[2]);
-    const double Rv = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pcol * p.Rs[2]);
-    f = Pv / Gv;
-    r = Rv / p.rad_e;
-  }
+  const double f = cell.P / cell.G;        // zero for padded columns
+  const double r = cell.R / p.rad_e;
   const int l0 = 32 * half;
   double val = f * ipow(r, lb * LBLK + l0 + 2);
 #pragma unroll 8
@@ -528,6 +586,8 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
   for (int i = 0; i < NP * 4; ++i) Cs[i * NTH + tid] = 0.0;
 
   const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
+  PressureCell cell;
+  if (MODE == MODE_PRESSURE) cell = load_pressure_cell<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
   for (int h = hfirst; h <= hlast; ++h) {
     // chunks of this ring that belong to the segment (partial rings are fine: the Legendre
     // weighting below is linear in the longitude partial sums)
@@ -541,10 +601,15 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
     for (int chunk = cbeg; chunk < cend; ++chunk) {
       if (MODE == MODE_PRESSURE)
-        produce_pressure<NTH>(p, seg.t, h, seg.lb, chunk, Bs);
+        produce_pressure<NTH>(p, cell, seg.lb, Bs);
       else
         produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs);
       __syncthreads();
+      if (MODE == MODE_PRESSURE) {
+        // the next unit's cell is fetched now, so its DRAM/L2 latency hides behind the contraction
+        const bool last = (chunk + 1 == p.nchunks);
+        cell = load_pressure_cell<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+      }
 
       if (MODE != MODE_PRESSURE) {
         // start pulling the next chunk's (or next ring's first chunk's) cube data into L2
@@ -733,6 +798,7 @@ struct mhb200_plan {
   int nlb, nmb, Mpad, ntiles, num_sms;
   Variant var[2];
   double *f1, *f2, *pmm, *sq, *rescale, *x, *w;
+  double* ckpt;            // Legendre restart states (nlb > 1)
   int* lb_first_tile_dev;
   std::vector<int> lb_first_tile;
   // per-call staging (field scales, long degree-factor vectors), grown on demand
@@ -933,6 +999,8 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
   gp.rescale = pl->rescale;
   gp.x = pl->x;
   gp.w = pl->w;
+  gp.ckpt = getenv("MHB200_NO_CKPT") ? nullptr : pl->ckpt;
+  gp.nlb = pl->nlb;
   gp.segs = v.sched.segs_dev;
   gp.cta_seg_begin = v.sched.cta_seg_begin_dev;
 }
@@ -1043,6 +1111,19 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
     delete pl;
     return rc;
   }
+  pl->ckpt = nullptr;
+  if (pl->nlb > 1) {
+    // Legendre restart states at the degree-block boundaries, computed once on the device
+    const size_t n = (size_t)nlat * pl->nlb * Mpad * 2;
+    MHB_CUDA(cudaMalloc((void**)&pl->ckpt, n * sizeof(double)));
+    MHB_CUDA(cudaMemset(pl->ckpt, 0, n * sizeof(double)));
+    dim3 grid((mmax + 64) / 64, nlat);
+    legendre_checkpoint_kernel<<<grid, 64>>>(nlat, lmax, mmax, Mpad, pl->nlb, pl->x, pl->f1, pl->f2, pl->pmm,
+                                             pl->sq, pl->ckpt);
+    g_launches.fetch_add(1);
+    MHB_CUDA(cudaGetLastError());
+    MHB_CUDA(cudaDeviceSynchronize());
+  }
   *out = pl;
   return MHB200_OK;
 }
@@ -1062,6 +1143,7 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   cudaFree(pl->x);
   cudaFree(pl->w);
   cudaFree(pl->lb_first_tile_dev);
+  if (pl->ckpt) cudaFree(pl->ckpt);
   if (pl->stage_dev) cudaFree(pl->stage_dev);
   delete pl;
   return MHB200_OK;
