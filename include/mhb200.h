@@ -118,6 +118,24 @@ int mhb200_atmosphere_stokes(const mhb200_plan* plan, int dtype,
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Host-buffer form of mhb200_atmosphere_stokes for one field: GPH and dP are HOST cubes
+ * (level, lat, lon) of type `dtype` (pinned memory gives full PCIe speed), clm/slm are HOST
+ * outputs of (lmax+1)*(mmax+1) doubles.  The latitude axis is cut into `nbands` (<= 16) bands
+ * and the host-to-device copy of band b+1 overlaps the kernel of band b.  The remaining
+ * operands are as above (device tables).  Size the workspace with
+ * mhb200_host_workspace_bytes(plan, nbands).  Returns after the results are on the host.
+ */
+size_t mhb200_host_workspace_bytes(const mhb200_plan* plan, int nbands);
+int mhb200_atmosphere_stokes_host(const mhb200_plan* plan, int dtype,
+                                  const void* GPH_host, const void* dP_host,
+                                  const double* geoid, const int64_t geoid_stride[2],
+                                  const double* ring_tab, const double* lon_tab,
+                                  int nlev, int nbands, int method, double rad_e,
+                                  const double* dfactor, const double* plm_table,
+                                  double* clm_host, double* slm_host,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * gen_point_pressure.py:126-154,160-194.  Scattered points with disc areas:
  *   C_lm + i S_lm = dfactor[l] * sum_p Pdisc_l(alpha_p) (P/G)_p (R_p/rad_e)^(l+2) Plm(cos th_p) e^{i m phi_p}
  * phi, theta, area are (npts) device arrays; P is (nbatch, npts); G and R are addressed

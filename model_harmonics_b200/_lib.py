@@ -39,6 +39,11 @@ PROTOTYPES = {
                                                 _c_int64_p, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_double, _c_double_p, _vp, _vp, _vp, _vp,
                                                 ctypes.c_size_t, _vp]),
+    'mhb200_host_workspace_bytes': (ctypes.c_size_t, [_vp, ctypes.c_int]),
+    'mhb200_atmosphere_stokes_host': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _c_int64_p, _vp, _vp,
+                                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                     _c_double_p, _vp, _c_double_p, _c_double_p, _vp,
+                                                     ctypes.c_size_t, _vp]),
     'mhb200_points_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'mhb200_point_pressure_f64': (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64,
                                                  _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,

@@ -29,6 +29,9 @@ const char* mhb200_last_error(void) { return mhb::err_buf(); }
 uint64_t mhb200_launch_count(void) { return (uint64_t)mhb::g_launches.load(); }
 
 int mhb200_device_check(int device) {
+  // cudaGetDeviceProperties costs milliseconds: remember a positive verdict per device
+  static std::atomic<int> ok_cache[64];
+  if (device >= 0 && device < 64 && ok_cache[device].load() == 1) return MHB200_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0) {
@@ -50,6 +53,7 @@ int mhb200_device_check(int device) {
     mhb::set_err("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     return MHB200_ENODEVICE;
   }
+  if (device < 64) ok_cache[device].store(1);
   return MHB200_OK;
 }
 

@@ -40,6 +40,7 @@ constexpr int PLM_PITCH = 65;
 constexpr int CS_ROWS = 36;       // per-thread accumulators kept in shared memory
 constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
 constexpr int DF_MAX = 448;
+constexpr int MAX_PARTS = 16;
 constexpr int LEV_GROUP = 40;     // levels staged per geometry pass
 
 // CTA shape.  NTH threads handle chunks of up to NTH/2 longitudes.  NTH = 256 runs one CTA per
@@ -94,6 +95,11 @@ struct ReduceParams {
   const double* slots;
   const double* dfactor_dev;    // used when lmax+1 > DF_MAX
   double *clm, *slm;
+  // a call may be split into parts (latitude bands of the host-pipelined path), each with its own
+  // schedule: part i owns slots [slot_off[i], ...) indexed by its own tile_slot_begin table
+  int nparts;
+  const int* part_tsb[MAX_PARTS];
+  int slot_off[MAX_PARTS];
   double dfactor[DF_MAX];       // degree factors travel as kernel parameters
 };
 
@@ -748,12 +754,16 @@ __global__ void __launch_bounds__(256) stokes_reduce_kernel(const __grid_constan
     double c = 0.0, s = 0.0;
     if (m <= l && m < ncol) {
       const int tile = t * q.ntiles + q.lb_first_tile[lb] + mb;
-      const int b = q.tile_slot_begin[tile], e = q.tile_slot_begin[tile + 1];
+      for (int part = 0; part < q.nparts; ++part) {
+        const int* tsb = (q.nparts == 1) ? q.tile_slot_begin : q.part_tsb[part];
+        const int off = (q.nparts == 1) ? 0 : q.slot_off[part];
+        const int b = tsb[tile] + off, e = tsb[tile + 1] + off;
 #pragma unroll 4
-      for (int k = b + grp; k < e; k += 4) {
-        const double* slot = q.slots + (size_t)k * SLOT_DOUBLES;
-        c += slot[(l_local)*MBLK + ml];
-        s += slot[(LBLK + l_local) * MBLK + ml];
+        for (int k = b + grp; k < e; k += 4) {
+          const double* slot = q.slots + (size_t)k * SLOT_DOUBLES;
+          c += slot[(l_local)*MBLK + ml];
+          s += slot[(LBLK + l_local) * MBLK + ml];
+        }
       }
     }
     part[0][grp][ml] = c;
@@ -778,7 +788,7 @@ __global__ void __launch_bounds__(256) stokes_reduce_kernel(const __grid_constan
 using namespace mhb;
 
 struct Schedule {
-  int nbatch = -1, nlev = -1, mode = -1;
+  int nbatch = -1, nlev = -1, mode = -1, h0 = -1, h1 = -1;
   int ncta = 0, nseg = 0;
   Segment* segs_dev = nullptr;
   int* cta_seg_begin_dev = nullptr;
@@ -799,6 +809,15 @@ struct mhb200_plan {
   Variant var[2];
   double *f1, *f2, *pmm, *sq, *rescale, *x, *w;
   double* ckpt;            // Legendre restart states (nlb > 1)
+  // host-pipelined atmosphere path: per-band schedules, device cubes, copy stream
+  Schedule band_sched[MAX_PARTS];
+  void* cube_dev[2] = {nullptr, nullptr};
+  size_t cube_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t band_ev[MAX_PARTS] = {};
+  cudaEvent_t done_ev = nullptr;
+  double* out_dev = nullptr;      // 2 x (lmax+1)(mmax+1)
+  double* out_pinned = nullptr;
   int* lb_first_tile_dev;
   std::vector<int> lb_first_tile;
   // per-call staging (field scales, long degree-factor vectors), grown on demand
@@ -834,9 +853,17 @@ void free_schedule(Schedule& sc) {
 // Static schedule: the (field, tile, ring, chunk) work units are linearised and cut into
 // contiguous spans of equal cost, one span per CTA; a span is split into segments at tile
 // boundaries, and every segment owns one partial-sum slot.
+int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, int nlev, int mode, int h0,
+                         int h1);
+
 int build_schedule(mhb200_plan* pl, Variant& v, int nbatch, int nlev, int mode) {
-  Schedule& sc = v.sched;
-  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode) return MHB200_OK;
+  return build_schedule_range(pl, v, v.sched, nbatch, nlev, mode, 0, pl->nlat);
+}
+
+// schedule over the rings [h0, h1) only
+int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, int nlev, int mode, int h0,
+                         int h1) {
+  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode && sc.h0 == h0 && sc.h1 == h1) return MHB200_OK;
   free_schedule(sc);
   struct Tile { int lb, mb; double c; };
   std::vector<Tile> tiles;
@@ -844,7 +871,8 @@ int build_schedule(mhb200_plan* pl, Variant& v, int nbatch, int nlev, int mode) 
     for (int mb = 0; mb <= std::min(lb, pl->nmb - 1); ++mb)
       tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev)});
   // per-unit cost = per-ring cost / nchunks (only ratios matter)
-  const long long units_per_tile = (long long)pl->nlat * v.nchunks;
+  const long long units_per_tile = (long long)(h1 - h0) * v.nchunks;
+  const long long unit0 = (long long)h0 * v.nchunks;
   double per_field = 0.0;
   for (auto& tl : tiles) per_field += tl.c * units_per_tile;
   const double total = per_field * nbatch;
@@ -867,7 +895,7 @@ int build_schedule(mhb200_plan* pl, Variant& v, int nbatch, int nlev, int mode) 
         if (cta == ncta - 1) take = units_per_tile - u;
         take = std::max<long long>(0, std::min<long long>(take, units_per_tile - u));
         if (take > 0) {
-          segs.push_back({t, tiles[ti].lb, tiles[ti].mb, (int)u, (int)(u + take), 0});
+          segs.push_back({t, tiles[ti].lb, tiles[ti].mb, (int)(unit0 + u), (int)(unit0 + u + take), 0});
           u += take;
           done += take * c;
         }
@@ -894,6 +922,8 @@ int build_schedule(mhb200_plan* pl, Variant& v, int nbatch, int nlev, int mode) 
   sc.nbatch = nbatch;
   sc.nlev = nlev;
   sc.mode = mode;
+  sc.h0 = h0;
+  sc.h1 = h1;
   return MHB200_OK;
 }
 
@@ -970,6 +1000,7 @@ int finish_reduce(mhb200_plan* pl, const Variant& v, const double* dfactor, int 
   q.nmb = pl->nmb;
   q.ntiles = pl->ntiles;
   q.tile_slot_begin = v.sched.tile_slot_begin_dev;
+  q.nparts = 1;
   q.lb_first_tile = pl->lb_first_tile_dev;
   q.slots = slots;
   q.clm = clm;
@@ -1144,6 +1175,15 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   cudaFree(pl->w);
   cudaFree(pl->lb_first_tile_dev);
   if (pl->ckpt) cudaFree(pl->ckpt);
+  for (auto& sc : pl->band_sched) free_schedule(sc);
+  for (auto& c : pl->cube_dev)
+    if (c) cudaFree(c);
+  if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
+  for (auto& e : pl->band_ev)
+    if (e) cudaEventDestroy(e);
+  if (pl->done_ev) cudaEventDestroy(pl->done_ev);
+  if (pl->out_dev) cudaFree(pl->out_dev);
+  if (pl->out_pinned) cudaFreeHost(pl->out_pinned);
   if (pl->stage_dev) cudaFree(pl->stage_dev);
   delete pl;
   return MHB200_OK;
@@ -1153,6 +1193,13 @@ size_t mhb200_grid_workspace_bytes(const mhb200_plan* pl, int nbatch, int nlev) 
   (void)nlev;
   if (!pl || nbatch < 1) return 0;
   return max_segments(pl, nbatch) * SLOT_DOUBLES * sizeof(double);
+}
+
+size_t mhb200_host_workspace_bytes(const mhb200_plan* pl, int nbands) {
+  if (!pl || nbands < 1) return 0;
+  nbands = std::min(nbands, MAX_PARTS);
+  // every band is its own launch with its own segments
+  return (size_t)nbands * max_segments(pl, 1) * SLOT_DOUBLES * sizeof(double);
 }
 
 int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const int64_t Ps[3], const double* G,
@@ -1243,6 +1290,132 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
                                : launch_ring<MODE_ATM_SW02, float>(gp, v, st);
   if (rc != MHB200_OK) return rc;
   return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+}
+
+
+// Host-buffer form of mhb200_atmosphere_stokes for ONE field: GPH and dP are HOST cubes
+// (level, lat, lon); clm/slm are HOST outputs.  The latitude axis is cut into `nbands` bands; the
+// copy of band b+1 (cudaMemcpy2DAsync on a private stream) overlaps the ring kernel of band b on
+// `stream` -- ring contributions are additive -- and one reduce over all bands' slots finishes.
+// The call returns when clm/slm are on the host.  Pinned host cubes give full PCIe speed.
+int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void* GPH_host, const void* dP_host,
+                                  const double* geoid, const int64_t geoid_stride[2], const double* ring_tab,
+                                  const double* lon_tab, int nlev, int nbands, int method, double rad_e,
+                                  const double* dfactor, const double* plm_table, double* clm_host,
+                                  double* slm_host, void* workspace, size_t workspace_bytes, void* stream) {
+  mhb200_plan* pl = const_cast<mhb200_plan*>(cpl);
+  if (!pl || !GPH_host || !dP_host || !ring_tab || !lon_tab || nlev < 1 || !dfactor || !clm_host || !slm_host ||
+      !workspace || (dtype != MHB200_F64 && dtype != MHB200_F32) ||
+      (method != MHB200_METHOD_BC05 && method != MHB200_METHOD_SW02) || (geoid && !geoid_stride)) {
+    set_err("mhb200_atmosphere_stokes_host: bad argument");
+    return MHB200_EINVAL;
+  }
+  nbands = std::max(1, std::min(std::min(nbands, MAX_PARTS), pl->nlat));
+  if (workspace_bytes < mhb200_host_workspace_bytes(pl, nbands)) {
+    set_err("mhb200_atmosphere_stokes_host: workspace too small (see mhb200_host_workspace_bytes)");
+    return MHB200_EWORKSPACE;
+  }
+  std::lock_guard<std::mutex> lock(pl->mu);
+  cudaStream_t st = (cudaStream_t)stream;
+  MHB_CUDA(cudaSetDevice(pl->device));
+  const int mode = (method == MHB200_METHOD_BC05) ? MODE_ATM_BC05 : MODE_ATM_SW02;
+  Variant& v = pl->var[pick_variant(pl, mode)];
+  const size_t isz = (dtype == MHB200_F64) ? 8 : 4;
+  const size_t plane = (size_t)pl->nlat * pl->nlon * isz, need = plane * nlev;
+  const size_t nout = (size_t)(pl->lmax + 1) * (pl->mmax + 1);
+  int rc;
+  if (pl->cube_bytes < need) {
+    MHB_CUDA(cudaDeviceSynchronize());
+    for (auto& c : pl->cube_dev) {
+      if (c) cudaFree(c);
+      c = nullptr;
+      MHB_CUDA(cudaMalloc(&c, need));
+    }
+    pl->cube_bytes = need;
+  }
+  if (!pl->copy_stream) {
+    MHB_CUDA(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : pl->band_ev) MHB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MHB_CUDA(cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
+    MHB_CUDA(cudaMalloc((void**)&pl->out_dev, 2 * nout * sizeof(double)));
+    MHB_CUDA(cudaMallocHost((void**)&pl->out_pinned, 2 * nout * sizeof(double)));
+  }
+  // the previous call's kernels (on `stream`) must be done with the device cubes before they are overwritten
+  MHB_CUDA(cudaEventRecord(pl->done_ev, st));
+  MHB_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->done_ev, 0));
+  pl->stage_reserved = 0;
+
+  GridParams gp;
+  ReduceParams q;
+  q.nparts = nbands;
+  int slot_off = 0;
+  for (int b = 0; b < nbands; ++b) {
+    const int h0 = (int)((long long)pl->nlat * b / nbands), h1 = (int)((long long)pl->nlat * (b + 1) / nbands);
+    // band copy: nlev rows of (h1-h0)*nlon elements, pitch = one (lat, lon) plane
+    const size_t off = (size_t)h0 * pl->nlon * isz, width = (size_t)(h1 - h0) * pl->nlon * isz;
+    MHB_CUDA(cudaMemcpy2DAsync((char*)pl->cube_dev[0] + off, plane, (const char*)GPH_host + off, plane, width,
+                               nlev, cudaMemcpyHostToDevice, pl->copy_stream));
+    MHB_CUDA(cudaMemcpy2DAsync((char*)pl->cube_dev[1] + off, plane, (const char*)dP_host + off, plane, width,
+                               nlev, cudaMemcpyHostToDevice, pl->copy_stream));
+    MHB_CUDA(cudaEventRecord(pl->band_ev[b], pl->copy_stream));
+    MHB_CUDA(cudaStreamWaitEvent(st, pl->band_ev[b], 0));
+    Schedule& sc = pl->band_sched[b];
+    if ((rc = build_schedule_range(pl, v, sc, 1, nlev, mode, h0, h1)) != MHB200_OK) return rc;
+    fill_plan_params(pl, v, gp);
+    gp.segs = sc.segs_dev;
+    gp.cta_seg_begin = sc.cta_seg_begin_dev;
+    gp.plm_table = plm_table;
+    gp.slots = (double*)workspace + (size_t)slot_off * SLOT_DOUBLES;
+    gp.GPH = pl->cube_dev[0];
+    gp.dP = pl->cube_dev[1];
+    gp.batch_stride = 0;
+    gp.field_scale = nullptr;
+    gp.geoid = geoid;
+    gp.geo_s0 = geoid ? geoid_stride[0] : 0;
+    gp.geo_s1 = geoid ? geoid_stride[1] : 0;
+    gp.ring_tab = ring_tab;
+    gp.lon_tab = lon_tab;
+    gp.nlev = nlev;
+    gp.rad_e = rad_e;
+    Variant vb = v;           // launch with this band's CTA count
+    vb.sched.ncta = sc.ncta;
+    if (mode == MODE_ATM_BC05)
+      rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_BC05, double>(gp, vb, st)
+                                 : launch_ring<MODE_ATM_BC05, float>(gp, vb, st);
+    else
+      rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_SW02, double>(gp, vb, st)
+                                 : launch_ring<MODE_ATM_SW02, float>(gp, vb, st);
+    if (rc != MHB200_OK) return rc;
+    q.part_tsb[b] = sc.tile_slot_begin_dev;
+    q.slot_off[b] = slot_off;
+    slot_off += sc.nseg;
+  }
+  // one reduce over all bands' slots
+  q.dfactor_dev = nullptr;
+  if (pl->lmax + 1 <= DF_MAX) {
+    for (int l = 0; l <= pl->lmax; ++l) q.dfactor[l] = dfactor[l];
+  } else {
+    if ((rc = ensure_stage(pl, (size_t)pl->lmax + 1)) != MHB200_OK) return rc;
+    if ((rc = stage(pl, dfactor, (size_t)pl->lmax + 1, 0, st)) != MHB200_OK) return rc;
+    q.dfactor_dev = pl->stage_dev;
+  }
+  q.lmax = pl->lmax;
+  q.mmax = pl->mmax;
+  q.nmb = pl->nmb;
+  q.ntiles = pl->ntiles;
+  q.tile_slot_begin = pl->band_sched[0].tile_slot_begin_dev;
+  q.lb_first_tile = pl->lb_first_tile_dev;
+  q.slots = (const double*)workspace;
+  q.clm = pl->out_dev;
+  q.slm = pl->out_dev + nout;
+  stokes_reduce_kernel<<<dim3(pl->lmax + 1, 1), 256, 0, st>>>(q);
+  g_launches.fetch_add(1);
+  MHB_CUDA(cudaGetLastError());
+  MHB_CUDA(cudaMemcpyAsync(pl->out_pinned, pl->out_dev, 2 * nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MHB_CUDA(cudaStreamSynchronize(st));
+  memcpy(clm_host, pl->out_pinned, nout * sizeof(double));
+  memcpy(slm_host, pl->out_pinned + nout, nout * sizeof(double));
+  return MHB200_OK;
 }
 
 }  // extern "C"

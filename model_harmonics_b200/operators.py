@@ -263,6 +263,41 @@ def _cube_pair(GPH, pressure, device):
     return g.contiguous(), d.contiguous()
 
 
+_HOST_BANDS = 8
+
+
+def _host_cube_pair(GPH, pressure):
+    """Both cubes as C-contiguous host arrays of one storage type (float64, or float32 as stored), else None."""
+    if isinstance(GPH, torch.Tensor) or isinstance(pressure, torch.Tensor):
+        return None
+    g = np.ma.getdata(GPH) if isinstance(GPH, np.ma.MaskedArray) else np.asarray(GPH)
+    d = np.ma.getdata(pressure) if isinstance(pressure, np.ma.MaskedArray) else np.asarray(pressure)
+    if g.shape != d.shape:
+        raise ValueError('GPH and pressure must have the same shape')
+    if not (g.dtype == np.float32 and d.dtype == np.float32):
+        g = g.astype(np.float64, copy=False)
+        d = d.astype(np.float64, copy=False)
+    return np.ascontiguousarray(g), np.ascontiguousarray(d)
+
+
+def _atmosphere_host(plan, g, d, geoid_t, geoid_strides, ring_t, lon_t, nlev, method, rad_e, dfactor, plm_tab):
+    L = _lib.lib()
+    clm = np.empty((plan.lmax + 1, plan.mmax + 1))
+    slm = np.empty((plan.lmax + 1, plan.mmax + 1))
+    ws = plan.host_workspace(_HOST_BANDS)
+    dfactor = np.ascontiguousarray(dfactor, dtype=np.float64)
+    dtype = _lib.F32 if g.dtype == np.float32 else _lib.F64
+    with plan.lock:
+        rc = L.mhb200_atmosphere_stokes_host(plan.handle, dtype, ctypes.c_void_p(g.ctypes.data),
+                                             ctypes.c_void_p(d.ctypes.data), _ptr(geoid_t),
+                                             _lib.int64x(*geoid_strides), _ptr(ring_t), _ptr(lon_t), int(nlev),
+                                             _HOST_BANDS, int(method), float(rad_e), _lib.as_double_p(dfactor),
+                                             _ptr(plm_tab), _lib.as_double_p(clm), _lib.as_double_p(slm),
+                                             _ptr(ws), ws.numel(), _stream_ptr())
+    _lib.check(rc, 'mhb200_atmosphere_stokes_host')
+    return clm, slm
+
+
 def gen_atmosphere_stokes(GPH, pressure, lon, lat, LMAX=60, MMAX=None, ELLIPSOID=None, GEOID=None,
                           WEIGHT=None, PLM=None, LOVE=None, METHOD='BC05'):
     """
@@ -277,6 +312,12 @@ def gen_atmosphere_stokes(GPH, pressure, lon, lat, LMAX=60, MMAX=None, ELLIPSOID
         raise ValueError('GPH must be (level, lat, lon)')
     LMAX, MMAX, plan, ring_t, lon_t, plm_tab, geoid_t, gstr, rad_e, dfactor = _atmosphere_prepare(
         shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGHT, PLM, LOVE, device)
+    host = _host_cube_pair(GPH, pressure)
+    if host is not None and shape[1] >= 2 * _HOST_BANDS:
+        # host cubes: latitude-band pipeline (copy of band b+1 overlaps the kernel of band b)
+        clm, slm = _atmosphere_host(plan, host[0], host[1], geoid_t, gstr, ring_t, lon_t, shape[0], method,
+                                    rad_e, dfactor, plm_tab)
+        return _make_harmonics(clm, slm, LMAX, MMAX)
     g, d = _cube_pair(GPH, pressure, device)
     clm, slm = _atmosphere_core(plan, g, d, 0, None, geoid_t, gstr, ring_t, lon_t, shape[0], 1, method,
                                 rad_e, dfactor, plm_tab)

@@ -64,6 +64,12 @@ class GridPlan(object):
             self._workspace = torch.empty(need, dtype=torch.uint8, device='cuda:%d' % self.device)
         return self._workspace
 
+    def host_workspace(self, nbands):
+        need = _lib.lib().mhb200_host_workspace_bytes(self.handle, int(nbands))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device='cuda:%d' % self.device)
+        return self._workspace
+
     def close(self):
         if getattr(self, 'handle', None) is not None and self.handle.value:
             try:
