@@ -67,6 +67,11 @@ struct Segment {
 
 struct GridParams {
   int nlat, nlon, lmax, mmax, Mpad, kc, nchunks, nks_total;
+  // longitude mirror folding (see build_variant): kc thread columns per chunk hold kcf folded
+  // columns -- first half the columns p, second half their mirrors q (phi_q = -phi_p mod 2 pi);
+  // unfolded: kcf == kc.  phys[chunk*kc + col] is the grid column of a thread column, or -1.
+  int kcf, half_off, fold;
+  const int* phys;
   const double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
   const double* plm_table;
   const double* ckpt;          // Legendre restart states [nlat][nlb][Mpad][2] (nlb > 1), else null
@@ -223,6 +228,26 @@ __device__ __forceinline__ int bs_index(int l_local, int col) {
 // Produce phase, pressure:  B[p,l] = (P/G) * (R/rad_e)^(l+2)   (gen_pressure_stokes.py:200)
 // A column is shared by two threads (warps w and w + NW/2): each handles 32 of the 64 degrees.
 // ---------------------------------------------------------------------------------------
+// slot of (degree, thread column) in the chunk buffer: folded chunks keep the columns p in the
+// first half-buffer and their mirrors in the second, both fragment-major over the folded index
+__device__ __forceinline__ int b_slot(const GridParams& p, int l_local, int col) {
+  const int hf = (col >= p.kcf) ? 1 : 0;
+  return hf * p.half_off + bs_index(l_local, col - hf * p.kcf);
+}
+
+// In-place fold of a produced chunk: first half <- B_p + B_q, second half <- B_p - B_q, so that
+//   sum_p cos(m phi_p) B_p = sum_j cos(m phi_j) (B_p + B_q),  sum_p sin(m phi_p) B_p = sum_j sin(m phi_j) (B_p - B_q)
+// over half as many columns (cos is even and sin odd under phi -> -phi).
+template <int NTH>
+__device__ __forceinline__ void fold_chunk(const GridParams& p, double* Bs) {
+  const int n = (p.kcf >> 2) * 256;          // doubles per half-buffer
+  for (int i = threadIdx.x; i < n; i += NTH) {
+    const double a = Bs[i], b = Bs[i + p.half_off];
+    Bs[i] = a + b;
+    Bs[i + p.half_off] = a - b;
+  }
+}
+
 // values of one grid cell for the pressure produce phase, loaded one chunk ahead
 struct PressureCell {
   double P, G, R;
@@ -232,12 +257,12 @@ __device__ __forceinline__ PressureCell load_pressure_cell(const GridParams& p, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWH = NTH / 64;
   const int col = (warp % NWH) * 32 + lane;
-  const int pcol = chunk * p.kc + col;
   PressureCell c;
   c.P = 0.0;
   c.G = 1.0;
   c.R = p.rad_e;
-  if (col < p.kc && pcol < p.nlon && h < p.nlat) {
+  const int pcol = (col < p.kc && h < p.nlat && chunk < p.nchunks) ? __ldg(p.phys + chunk * p.kc + col) : -1;
+  if (pcol >= 0) {
     c.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pcol * p.Ps[2]);
     c.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pcol * p.Gs[2]);
     c.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pcol * p.Rs[2]);
@@ -257,7 +282,7 @@ __device__ __forceinline__ void produce_pressure(const GridParams& p, const Pres
   double val = f * ipow(r, lb * LBLK + l0 + 2);
 #pragma unroll 8
   for (int j = 0; j < 32; ++j) {
-    Bs[bs_index(l0 + j, col)] = val;
+    Bs[b_slot(p, l0 + j, col)] = val;
     val *= r;
   }
 }
@@ -419,8 +444,8 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
   }
   // geometry-pass ownership: a fixed column, levels of parity tid / KC
   const int gcol = tid & (KC - 1), gpar = tid / KC;
-  const int gpcol = chunk * p.kc + gcol;
-  const bool gactive = (gcol < p.kc) && (gpcol < p.nlon);
+  const int gpcol = (gcol < p.kc) ? __ldg(p.phys + chunk * p.kc + gcol) : -1;
+  const bool gactive = (gpcol >= 0);
   const int gpc = gactive ? gpcol : 0;
   ColumnGeom cg;
   {
@@ -537,7 +562,7 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
   if (acol < p.kc) {
     const int l0 = 32 * half;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) Bs[bs_index(l0 + j, acol)] = acc[j];
+    for (int j = 0; j < 32; ++j) Bs[b_slot(p, l0 + j, acol)] = acc[j];
   }
 }
 
@@ -545,18 +570,22 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 // contraction phase so that DRAM latency is off the critical path)
 template <typename Tin, int NTH>
 __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
-  if (h >= p.nlat) return;
-  const size_t lev_stride = (size_t)p.nlat * p.nlon;
+  if (h >= p.nlat || chunk >= p.nchunks) return;
+  const int col = threadIdx.x;
+  if (col >= p.kc) return;
   const int per_line = 128 / (int)sizeof(Tin);
-  const int lines = (p.kc + per_line - 1) / per_line + 1;
-  const size_t base = (size_t)t * p.batch_stride + (size_t)h * p.nlon + (size_t)chunk * p.kc;
-  for (int i = threadIdx.x; i < p.nlev * lines * 2; i += NTH) {
-    const int arr = i & 1, j = i >> 1;
-    const int k = j / lines, ln = j % lines;
-    const int col = min(ln * per_line, p.kc - 1);
-    if ((size_t)chunk * p.kc + col >= (size_t)p.nlon) continue;
-    const Tin* q = (const Tin*)(arr ? p.dP : p.GPH) + base + (size_t)k * lev_stride + col;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  const int pc = __ldg(p.phys + chunk * p.kc + col);
+  if (pc < 0) return;
+  // one thread per 128-byte line: the first thread column that falls into it
+  const int prev = (col > 0) ? __ldg(p.phys + chunk * p.kc + col - 1) : -1;
+  if (prev >= 0 && (prev / per_line) == (pc / per_line)) return;
+  const size_t lev_stride = (size_t)p.nlat * p.nlon;
+  const size_t base = (size_t)t * p.batch_stride + (size_t)h * p.nlon + pc;
+  const Tin* g = (const Tin*)p.GPH + base;
+  const Tin* d = (const Tin*)p.dP + base;
+  for (int k = 0; k < p.nlev; ++k) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)k * lev_stride));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)k * lev_stride));
   }
 }
 
@@ -582,7 +611,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
   const int gA = DIAG ? (warp & 3) : warp;
   const int gB = DIAG ? (7 - gA) : warp;
   const int nA = DIAG ? (8 - gA) : 8;
-  const int nksc = p.kc >> 2;
+  const int nksc = p.kcf >> 2;        // contraction k-steps per chunk
 
   int lt[NP];          // degree tile of pair j
 #pragma unroll
@@ -611,6 +640,10 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
       else
         produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs);
       __syncthreads();
+      if (p.fold) {
+        fold_chunk<NTH>(p, Bs);
+        __syncthreads();
+      }
       if (MODE == MODE_PRESSURE) {
         // the next unit's cell is fetched now, so its DRAM/L2 latency hides behind the contraction
         const bool last = (chunk + 1 == p.nchunks);
@@ -638,45 +671,44 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
           a[3] = __ldg(ap + (gB * 2 + 1) * 32);
         }
       };
+      // B fragments: cosine rows contract with the first half-buffer (B_p + B_q when folded), sine
+      // rows with the second (B_p - B_q); unfolded chunks have a single buffer (half_off = 0)
       const int brot = lane >> 2, bcol = lane & 3;
-      auto load_b = [&](double(&b)[NP], int k) {
-        const int kc2 = min(k, klast);
-        const double* Bk = Bs + kc2 * 256 + (((brot + kc2) & 7) << 2) + bcol;
+      const double* Bsin = Bs + (p.fold ? p.half_off : 0);
+      auto mma_step = [&](const double(&c)[NA], int k) {
+        const int boff = k * 256 + (((brot + k) & 7) << 2) + bcol;
+        double bc[NP], bs[NP];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) b[j] = Bk[lt[j] * 32];
-      };
-      auto mma_step = [&](const double(&c)[NA], const double(&bb)[NP]) {
+        for (int j = 0; j < NP; ++j) {
+          bc[j] = Bs[boff + lt[j] * 32];
+          bs[j] = Bsin[boff + lt[j] * 32];
+        }
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           const bool first = (!DIAG) || (j < nA);
-          dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], bb[j]);
-          dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], bb[j]);
+          dmma884(acc[j][0][0], acc[j][0][1], first ? c[0] : c[DIAG ? 2 : 0], bc[j]);
+          dmma884(acc[j][1][0], acc[j][1][1], first ? c[1] : c[DIAG ? 3 : 1], bs[j]);
         }
       };
-      double a[4][NA], b[2][NP];
+      double a[4][NA];
       const int k0 = sub;
 #pragma unroll
       for (int i = 0; i < 3; ++i) load_a(a[i], k0 + i * KSTRIDE);
-      load_b(b[0], k0);
-      // 4-deep trig ring / 2-deep B ring, fully unrolled: no rotation copies.  Main loop: groups
-      // of four k-steps with no guards; tail: the remaining (< 4) k-steps.
+      // 4-deep trig ring, fully unrolled: no rotation copies.  Main loop: groups of four k-steps
+      // with no guards; tail: the remaining (< 4) k-steps.
       int ks = k0;
       for (; ks + 3 * KSTRIDE < nksc; ks += 4 * KSTRIDE) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int k = ks + u * KSTRIDE;
           load_a(a[(u + 3) & 3], k + 3 * KSTRIDE);
-          load_b(b[(u + 1) & 1], k + KSTRIDE);
-          mma_step(a[u], b[u & 1]);
+          mma_step(a[u], k);
         }
       }
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         const int k = ks + u * KSTRIDE;
-        if (k < nksc) {
-          load_b(b[(u + 1) & 1], k + KSTRIDE);
-          mma_step(a[u], b[u & 1]);
-        }
+        if (k < nksc) mma_step(a[u], k);
       }
       __syncthreads();
     }
@@ -798,8 +830,9 @@ struct Schedule {
 // longitude chunking + trig table for one CTA shape (variant 0: 256 threads, 1: 128 threads)
 struct Variant {
   int nth = 0, ctas_per_sm = 1;
-  int kc = 0, nchunks = 0, nks_total = 0;
+  int kc = 0, kcf = 0, nchunks = 0, nks_total = 0;   // thread columns / contraction columns per chunk
   double* trig = nullptr;
+  int* phys = nullptr;                               // [nchunks][kc] grid column of each thread column
   Schedule sched;
 };
 
@@ -809,6 +842,10 @@ struct mhb200_plan {
   Variant var[2];
   double *f1, *f2, *pmm, *sq, *rescale, *x, *w;
   double* ckpt;            // Legendre restart states (nlb > 1)
+  // longitude mirror folding: contraction column i pairs grid column colp[i] with its mirror
+  // colq[i] (phi_q = -phi_p mod 2 pi; colq == colp for a self-mirrored column)
+  bool fold = false;
+  std::vector<int> colp, colq;
   // host-pipelined atmosphere path: per-band schedules, device cubes, copy stream
   Schedule band_sched[MAX_PARTS];
   void* cube_dev[2] = {nullptr, nullptr};
@@ -837,8 +874,8 @@ int upload(T** dev, const std::vector<T>& host) {
 }
 
 // fp64-pipe cost (arbitrary units per longitude) of one ring of one tile
-double ring_cost(bool diag, int mode, int nlev) {
-  const double mma = diag ? 4608.0 : 8192.0;
+double ring_cost(bool diag, int mode, int nlev, bool fold) {
+  const double mma = (diag ? 4608.0 : 8192.0) * (fold ? 0.5 : 1.0);
   const double prod = (mode == MODE_PRESSURE) ? 90.0 : (double)nlev * 136.0;
   return mma + prod;
 }
@@ -869,7 +906,7 @@ int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, 
   std::vector<Tile> tiles;
   for (int lb = 0; lb < pl->nlb; ++lb)
     for (int mb = 0; mb <= std::min(lb, pl->nmb - 1); ++mb)
-      tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev)});
+      tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev, pl->fold)});
   // per-unit cost = per-ring cost / nchunks (only ratios matter)
   const long long units_per_tile = (long long)(h1 - h0) * v.nchunks;
   const long long unit0 = (long long)h0 * v.nchunks;
@@ -1020,6 +1057,10 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
   gp.mmax = pl->mmax;
   gp.Mpad = pl->Mpad;
   gp.kc = v.kc;
+  gp.kcf = v.kcf;
+  gp.fold = pl->fold ? 1 : 0;
+  gp.half_off = pl->fold ? (v.kcf / 4) * 256 : 0;
+  gp.phys = v.phys;
   gp.nchunks = v.nchunks;
   gp.nks_total = v.nks_total;
   gp.trig = v.trig;
@@ -1037,27 +1078,116 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
 }
 
 // trig table, fragment-major [mb][kstep][16 row tiles][32 lanes]  (m_phi, gen_pressure_stokes.py:176-177)
+// Pairs every longitude with its mirror (phi_q = -phi_p mod 2 pi).  Regular grids have one; then
+// cos(m phi) is shared by the pair and sin(m phi) flips sign, and the Fourier contraction runs over
+// half the columns.  The match must be exact to a few ulp of 2 pi: the fold assumes
+// cos(m phi_q) == cos(m phi_p), and a mismatch delta costs m*delta.
+void find_mirrors(mhb200_plan* pl, const double* phi) {
+  const int n = pl->nlon;
+  const double two_pi = 6.283185307179586;
+  const double tol = 4.0 * 8.9e-16;
+  std::vector<int> mirror(n, -1);
+  std::vector<std::pair<double, int>> key(n);
+  for (int p = 0; p < n; ++p) {
+    double a = fmod(phi[p], two_pi);
+    if (a < 0) a += two_pi;
+    key[p] = {a, p};
+  }
+  std::sort(key.begin(), key.end());
+  bool ok = true;
+  for (int p = 0; p < n && ok; ++p) {
+    double want = fmod(-phi[p], two_pi);
+    if (want < 0) want += two_pi;
+    // nearest key (also across the 0 / 2 pi seam)
+    auto it = std::lower_bound(key.begin(), key.end(), std::make_pair(want, -1));
+    int best = -1;
+    double bestd = 1e300;
+    for (int d = -1; d <= 0; ++d) {
+      long long i = (it - key.begin()) + d;
+      const int idx = (int)((i % n + n) % n);
+      double diff = fabs(key[idx].first - want);
+      diff = std::min(diff, two_pi - diff);
+      if (diff < bestd) {
+        bestd = diff;
+        best = key[idx].second;
+      }
+    }
+    if (best < 0 || bestd > tol) ok = false;
+    else mirror[p] = best;
+  }
+  for (int p = 0; p < n && ok; ++p)
+    if (mirror[mirror[p]] != p) ok = false;
+  if (getenv("MHB200_NO_FOLD")) ok = false;
+  pl->fold = ok;
+  pl->colp.clear();
+  pl->colq.clear();
+  if (ok) {
+    std::vector<char> used(n, 0);
+    for (int p = 0; p < n; ++p) {
+      if (used[p]) continue;
+      used[p] = used[mirror[p]] = 1;
+      pl->colp.push_back(p);
+      pl->colq.push_back(mirror[p]);
+    }
+  } else {
+    for (int p = 0; p < n; ++p) {
+      pl->colp.push_back(p);
+      pl->colq.push_back(-1);
+    }
+  }
+}
+
+// chunking, thread-column map and trig table (fragment-major [mb][kstep][16 row tiles][32 lanes];
+// m_phi of gen_pressure_stokes.py:176-177 restricted to the contraction columns) for one CTA shape
 int build_variant(mhb200_plan* pl, Variant& v, int nth, const double* phi) {
   v.nth = nth;
   v.ctas_per_sm = 256 / nth;
-  const int kcmax = nth / 2;
-  v.nchunks = (pl->nlon + kcmax - 1) / kcmax;
-  v.kc = (((pl->nlon + v.nchunks - 1) / v.nchunks) + 7) / 8 * 8;
-  v.nks_total = v.nchunks * (v.kc / 4);
+  const int nf = (int)pl->colp.size();                 // contraction columns
+  const int kcf_max = pl->fold ? nth / 4 : nth / 2;
+  // number of chunks: the smallest, or up to two more when that wastes less padding
+  const int nmin = (nf + kcf_max - 1) / kcf_max;
+  long long best_pad = -1;
+  for (int nc = nmin; nc <= nmin + 2; ++nc) {
+    const int k = (((nf + nc - 1) / nc) + 7) / 8 * 8;
+    if (k > kcf_max) continue;
+    const long long pad = (long long)nc * k;
+    if (best_pad < 0 || pad < best_pad) {
+      best_pad = pad;
+      v.nchunks = nc;
+      v.kcf = k;
+    }
+  }
+  v.kc = pl->fold ? 2 * v.kcf : v.kcf;
+  const int nksc = v.kcf / 4;
+  v.nks_total = v.nchunks * nksc;
+  std::vector<int> phys((size_t)v.nchunks * v.kc, -1);
+  for (int c = 0; c < v.nchunks; ++c)
+    for (int j = 0; j < v.kcf; ++j) {
+      const int idx = c * v.kcf + j;
+      if (idx >= nf) continue;
+      phys[(size_t)c * v.kc + j] = pl->colp[idx];
+      if (pl->fold) phys[(size_t)c * v.kc + v.kcf + j] = pl->colq[idx];
+    }
   std::vector<double> trig((size_t)pl->nmb * v.nks_total * 512, 0.0);
   for (int mb = 0; mb < pl->nmb; ++mb)
     for (int ks = 0; ks < v.nks_total; ++ks)
       for (int g = 0; g < 8; ++g)
         for (int lane = 0; lane < 32; ++lane) {
           const int m = mb * MBLK + g * 8 + (lane >> 2);
-          const int p = ks * 4 + (lane & 3);
-          if (m > pl->mmax || p >= pl->nlon) continue;
+          const int c = ks / nksc, jloc = (ks % nksc) * 4 + (lane & 3);
+          const int idx = c * v.kcf + jloc;
+          if (m > pl->mmax || idx >= nf) continue;
+          const int p = pl->colp[idx];
+          // a self-mirrored column appears in both half-buffers: halve it (its sine part cancels)
+          const double wc = (pl->fold && pl->colq[idx] == p) ? 0.5 : 1.0;
           const double arg = (double)m * phi[p];
           const size_t base = (((size_t)mb * v.nks_total + ks) * 16 + g * 2) * 32 + lane;
-          trig[base] = cos(arg);
+          trig[base] = wc * cos(arg);
           trig[base + 32] = sin(arg);
         }
-  return upload(&v.trig, trig);
+  int rc = upload(&v.trig, trig);
+  if (rc != MHB200_OK) return rc;
+  return upload(&v.phys, phys);
 }
 
 }  // namespace
@@ -1096,6 +1226,7 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   }
   pl->ntiles = nt;
 
+  find_mirrors(pl, phi);
   if ((rc = build_variant(pl, pl->var[0], 256, phi)) != MHB200_OK) { delete pl; return rc; }
   if (pl->nlb == 1 && (rc = build_variant(pl, pl->var[1], 128, phi)) != MHB200_OK) { delete pl; return rc; }
 
@@ -1164,6 +1295,7 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   cudaSetDevice(pl->device);
   for (auto& v : pl->var) {
     if (v.trig) cudaFree(v.trig);
+    if (v.phys) cudaFree(v.phys);
     free_schedule(v.sched);
   }
   cudaFree(pl->f1);
