@@ -270,6 +270,52 @@ __device__ __forceinline__ PressureCell load_pressure_cell(const GridParams& p, 
   return c;
 }
 
+// Folded chunks: four threads per folded column (16 degrees each) handle BOTH grid columns p and q
+// and store B_p + B_q / B_p - B_q directly -- no separate fold pass, and 16-step product chains.
+struct PressureCell2 {
+  PressureCell p, q;
+};
+template <int NTH>
+__device__ __forceinline__ PressureCell2 load_pressure_cell2(const GridParams& p, int t, int h, int chunk) {
+  const int j = threadIdx.x % (NTH / 4);
+  PressureCell2 c;
+  c.p.P = c.q.P = 0.0;
+  c.p.G = c.q.G = 1.0;
+  c.p.R = c.q.R = p.rad_e;
+  if (j < p.kcf && h < p.nlat && chunk < p.nchunks) {
+    const int pc = __ldg(p.phys + chunk * p.kc + j), qc = __ldg(p.phys + chunk * p.kc + p.kcf + j);
+    if (pc >= 0) {
+      c.p.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]);
+      c.p.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]);
+      c.p.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]);
+    }
+    if (qc >= 0) {
+      c.q.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + qc * p.Ps[2]);
+      c.q.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + qc * p.Gs[2]);
+      c.q.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + qc * p.Rs[2]);
+    }
+  }
+  return c;
+}
+template <int NTH>
+__device__ __forceinline__ void produce_pressure_folded(const GridParams& p, const PressureCell2& c, int lb,
+                                                        double* Bs) {
+  const int j = threadIdx.x % (NTH / 4), quarter = threadIdx.x / (NTH / 4);
+  if (j >= p.kcf) return;
+  const double fp = c.p.P / c.p.G, rp = c.p.R / p.rad_e;
+  const double fq = c.q.P / c.q.G, rq = c.q.R / p.rad_e;
+  const int l0 = 16 * quarter;
+  double vp = fp * ipow(rp, lb * LBLK + l0 + 2), vq = fq * ipow(rq, lb * LBLK + l0 + 2);
+#pragma unroll 8
+  for (int i = 0; i < 16; ++i) {
+    const int slot = bs_index(l0 + i, j);
+    Bs[slot] = vp + vq;
+    Bs[slot + p.half_off] = vp - vq;
+    vp *= rp;
+    vq *= rq;
+  }
+}
+
 template <int NTH>
 __device__ __forceinline__ void produce_pressure(const GridParams& p, const PressureCell& cell, int lb, double* Bs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -622,7 +668,12 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
   const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
   PressureCell cell;
-  if (MODE == MODE_PRESSURE) cell = load_pressure_cell<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+  PressureCell2 cell2;
+  const bool pfold = (MODE == MODE_PRESSURE) && p.fold;
+  if (MODE == MODE_PRESSURE) {
+    if (pfold) cell2 = load_pressure_cell2<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+    else cell = load_pressure_cell<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+  }
   for (int h = hfirst; h <= hlast; ++h) {
     // chunks of this ring that belong to the segment (partial rings are fine: the Legendre
     // weighting below is linear in the longitude partial sums)
@@ -635,19 +686,22 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
     for (int j = 0; j < NP; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
 
     for (int chunk = cbeg; chunk < cend; ++chunk) {
-      if (MODE == MODE_PRESSURE)
-        produce_pressure<NTH>(p, cell, seg.lb, Bs);
-      else
+      if (MODE == MODE_PRESSURE) {
+        if (pfold) produce_pressure_folded<NTH>(p, cell2, seg.lb, Bs);
+        else produce_pressure<NTH>(p, cell, seg.lb, Bs);
+      } else {
         produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs);
+      }
       __syncthreads();
-      if (p.fold) {
+      if (p.fold && !pfold) {
         fold_chunk<NTH>(p, Bs);
         __syncthreads();
       }
       if (MODE == MODE_PRESSURE) {
-        // the next unit's cell is fetched now, so its DRAM/L2 latency hides behind the contraction
+        // the next unit's cells are fetched now, so their DRAM/L2 latency hides behind the contraction
         const bool last = (chunk + 1 == p.nchunks);
-        cell = load_pressure_cell<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        if (pfold) cell2 = load_pressure_cell2<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        else cell = load_pressure_cell<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }
 
       if (MODE != MODE_PRESSURE) {
