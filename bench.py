@@ -436,6 +436,20 @@ def other_workloads(mh, syn, torch, L):
     ms = timeit(lambda: mh.pressure_stokes_batch(Pd, Gd, Rd, lon, lat, LMAX=360, LOVE=L3, as_numpy=False), 3, warm=1)
     out['pressure_c4'] = {'config': '721x1440, LMAX=360', 'ms': ms, 'fields_per_s': 1e3 / ms,
                           'algorithmic_tflops': 272e9 / ms / 1e9}
+    # 8f-2: upstream producer, T/q/sp on 37 levels of the 0.25 degree grid -> (Z, dp); HBM-bound stream
+    Tm, Qm, SPm, zs, A, B, AI, BI = syn.model_level_inputs(NLEV, NLAT, NLON, seed=11)
+    dvt = [torch.from_numpy(a).cuda() for a in (Tm, Qm, SPm)]
+    ms = timeit(lambda: mh.geopotential_levels(dvt[0], dvt[1], dvt[2], zs, A, B, AI, BI, divide_by=9.80665,
+                                               as_numpy=False), 10)
+    moved = 4 * 4 * NLEV * NLAT * NLON      # read T, q; write Z, dp (float32)
+    peaks = {}
+    if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')):
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    out['hypsometric_f2'] = {'config': '%dx%dx%d float32 T,q -> Z,dp' % (NLEV, NLAT, NLON), 'ms': ms,
+                             'fields_per_s': 1e3 / ms, 'algorithmic_bytes': moved,
+                             'roofline': {'bound': 'hbm', 'achieved': moved / ms / 1e6, 'peak': hbm, 'unit': 'GB/s',
+                                          'frac': moved / ms / 1e6 / hbm}}
     return out
 
 

@@ -151,6 +151,22 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
                               double* clm_out, double* slm_out,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Upstream producer of the atmosphere operator's inputs: hypsometric integration
+ * over hybrid model levels, reanalysis/reanalysis_geopotential_heights.py:349-383.
+ * T, Q            device float32 (nlev, ncol), bottom level first; ncol = nlat*nlon
+ * SP, gh0         device float32 (ncol): surface pressure, surface geopotential (geopotential*GRAVITY)
+ * A, B (nA), AI, BI (nAI)  host float64 hybrid coefficients at half levels / interfaces
+ * divisor         outputs Z / divisor in float32 (9.80665 gives geopotential height, 1 leaves m^2/s^2)
+ * Z_out, DIFF_out device float32 (nlev, ncol): geopotential at the levels, pressure difference
+ * Arithmetic follows the reference's mixed float32/float64 rounding step by step.
+ */
+int mhb200_geopotential_levels_f32(int device, const float* T, const float* Q, const float* SP,
+                                   const float* gh0, const double* A, const double* B, int nA,
+                                   const double* AI, const double* BI, int nAI, int nlev, int64_t ncol,
+                                   double R_dry, double Pmin, float divisor,
+                                   float* Z_out, float* DIFF_out, void* stream);
+
 /* counters for bench.py: kernels launched by this library since load (all threads) */
 uint64_t mhb200_launch_count(void);
 

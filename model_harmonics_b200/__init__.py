@@ -9,9 +9,10 @@ There is no CPU fallback.
 """
 from .operators import (gen_pressure_stokes, gen_atmosphere_stokes, gen_point_pressure,
                         pressure_stokes_batch, atmosphere_stokes_batch, point_pressure_batch)
+from .hypsometric import geopotential_levels
 from ._compat import harmonics, units
 
 __version__ = '0.1.0'
 __all__ = ['gen_pressure_stokes', 'gen_atmosphere_stokes', 'gen_point_pressure',
            'pressure_stokes_batch', 'atmosphere_stokes_batch', 'point_pressure_batch',
-           'harmonics', 'units']
+           'geopotential_levels', 'harmonics', 'units']

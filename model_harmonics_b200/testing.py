@@ -8,7 +8,7 @@ SURVEY.md section 8(d); every generator is seeded.
 import numpy as np
 
 __all__ = ['love_numbers', 'grid_axes', 'surface_geometry', 'pressure_fields',
-           'point_cloud', 'atmosphere_cube', 'atmosphere_field_scalars']
+           'point_cloud', 'atmosphere_cube', 'atmosphere_field_scalars', 'model_level_inputs']
 
 _WGS84_A = 6378137.0
 _WGS84_F = 1.0 / 298.257223563
@@ -97,3 +97,23 @@ def atmosphere_field_scalars(t):
     a = 1.0e-3 * np.sin(2.0 * np.pi * t / 12.0)
     b = 5.0e-3 * np.cos(2.0 * np.pi * t / 12.0) + 1.0e-5 * t
     return 1.0 + a, 1.0 + b
+
+
+def model_level_inputs(nlev, nlat, nlon, seed=1234, interfaces_extra=True):
+    """Seeded synthetic hybrid-level inputs (float32 T, q, sp; float64 coefficients), bottom level first."""
+    rng = np.random.default_rng(seed)
+    # hybrid coefficients: interface pressures p = AI + BI*sp falling from sp to ~0
+    eta = np.linspace(1.0, 0.0, nlev + 1)**1.6
+    BI = eta**1.5
+    AI = 1.0e5 * (eta - BI) + 5.0 * (1.0 - eta)
+    AI[-1] = 0.0
+    BI[-1] = 0.0
+    A = 0.5 * (AI[:-1] + AI[1:])
+    B = 0.5 * (BI[:-1] + BI[1:])
+    if not interfaces_extra:
+        AI, BI = AI[:-1], BI[:-1]
+    T = (288.0 - 60.0 * (1.0 - eta[:-1])[:, None, None] + 5.0 * rng.standard_normal((nlev, nlat, nlon))).astype(np.float32)
+    Q = np.abs(0.012 * eta[:-1, None, None]**3 * (1.0 + 0.3 * rng.standard_normal((nlev, nlat, nlon)))).astype(np.float32)
+    SP = (1.0e5 - 2.0e4 * np.abs(rng.standard_normal((nlat, nlon)))).astype(np.float32)
+    zs = (9.80665 * np.clip(1500.0 * rng.standard_normal((nlat, nlon)), 0.0, 6000.0)).astype(np.float32)
+    return T, Q, SP, zs, A, B, AI, BI

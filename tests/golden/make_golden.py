@@ -35,5 +35,15 @@ def main():
         print('%-28s %-22s max|clm|=%.3e  %s' % (name, func, np.abs(Y.clm).max(), Y.clm.shape))
 
 
+def hypsometric():
+    """tests/golden/hypsometric.npz: the reference's own loop lines executed on seeded inputs."""
+    from oracle import hypsometric_oracle as ho
+    case = dict(nlev=11, nlat=10, nlon=18, seed=20)
+    Z, D = ho.reference_loop(*ho.synthetic_model_levels(**case))
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'hypsometric.npz'), Z=Z, DIFF=D,
+                        source='reference lines 349-383 executed by oracle/hypsometric_oracle.reference_loop')
+
+
 if __name__ == '__main__':
     main()
+    hypsometric()
