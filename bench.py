@@ -438,8 +438,8 @@ def other_workloads(mh, syn, torch, L):
                           'algorithmic_tflops': 272e9 / ms / 1e9}
     # 8f-2: upstream producer, T/q/sp on 37 levels of the 0.25 degree grid -> (Z, dp); HBM-bound stream
     Tm, Qm, SPm, zs, A, B, AI, BI = syn.model_level_inputs(NLEV, NLAT, NLON, seed=11)
-    dvt = [torch.from_numpy(a).cuda() for a in (Tm, Qm, SPm)]
-    ms = timeit(lambda: mh.geopotential_levels(dvt[0], dvt[1], dvt[2], zs, A, B, AI, BI, divide_by=9.80665,
+    dvt = [torch.from_numpy(a).cuda() for a in (Tm, Qm, SPm, zs)]
+    ms = timeit(lambda: mh.geopotential_levels(dvt[0], dvt[1], dvt[2], dvt[3], A, B, AI, BI, divide_by=9.80665,
                                                as_numpy=False), 10)
     moved = 4 * 4 * NLEV * NLAT * NLON      # read T, q; write Z, dp (float32)
     peaks = {}

@@ -48,10 +48,17 @@ def geopotential_levels(T, Q, SP, geopotential, A, B, AI, BI, GRAVITY=1.0, R_dry
     t = _f32_dev(T, device)
     q = _f32_dev(Q, device, (nlev, nlat, nlon))
     sp = _f32_dev(SP, device, (nlat, nlon))
-    gh0 = np.empty((nlat, nlon), dtype=np.float32)
-    g = geopotential.cpu().numpy() if isinstance(geopotential, torch.Tensor) else np.asarray(geopotential)
-    gh0[:, :] = g * GRAVITY                                          # :349-351
-    gh0_t = torch.from_numpy(gh0).to('cuda:%d' % device)
+    if isinstance(geopotential, torch.Tensor) and geopotential.is_cuda:
+        # float32 array times a Python scalar stays float32 in NumPy; same single rounding here
+        gh0_t = (geopotential.to(torch.float32) * float(GRAVITY)).contiguous() if GRAVITY != 1.0 \
+            else geopotential.to(torch.float32).contiguous()
+    else:
+        gh0 = np.empty((nlat, nlon), dtype=np.float32)
+        g = geopotential.cpu().numpy() if isinstance(geopotential, torch.Tensor) else np.asarray(geopotential)
+        gh0[:, :] = g * GRAVITY                                          # :349-351
+        gh0_t = torch.from_numpy(gh0).to('cuda:%d' % device)
+    if tuple(gh0_t.shape) != (nlat, nlon):
+        raise ValueError('geopotential must be (nlat, nlon)')
     A, B, AI, BI = [np.ascontiguousarray(np.ma.getdata(v), dtype=np.float64) for v in (A, B, AI, BI)]
     if len(A) != len(B) or len(AI) != len(BI):
         raise ValueError('hybrid coefficient vectors must pair up')
