@@ -46,6 +46,7 @@ struct PointParams {
   double rad_e, area_denom;     // 2*pi*rad_e^2 formed on the host as the reference does
   double* W;                    // [nbatch][lmax+1][npad]
   double* xg;                   // [npad] cos(theta)
+  double2* E;                   // [mmax+1][npad] (u^m/1e-280) * (cos m phi, sin m phi)
   // contraction
   const double *f1, *f2, *pmm, *sq;   // Holmes-Featherstone multipliers [(lmax+1)][Mpad]
   int Mpad;
@@ -91,6 +92,34 @@ __global__ void points_weights_kernel(const PointParams q) {
   }
 }
 
+// Per (point, order) factors of the contraction, one thread each (throughput-oriented: the
+// contraction kernel used to run these sincos / power chains serially in low-occupancy warps):
+//   E[m][p] = (u_p^m / 1e-280) * (cos(m phi_p), sin(m phi_p)),  u = sqrt(1 - x^2) (0 -> eps)
+// i.e. e^{i m phi} of gen_point_pressure.py:186-188 with the rescale of the scaled
+// Holmes-Featherstone column folded in.  grid (npad/128, mmax+1).
+__global__ void points_trig_kernel(const PointParams q) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (p >= q.npad) return;
+  double2 e = make_double2(0.0, 0.0);
+  if (p < q.npts) {
+    const double x = cos(q.theta[p]);
+    double u = sqrt(1.0 - x * x);
+    if (u == 0.0) u = 2.220446049250313e-16;
+    double r = (m == 0) ? 1.0 : 1.0e280, bb = u;
+    int k = m;
+    while (k) {
+      if (k & 1) r *= bb;
+      bb *= bb;
+      k >>= 1;
+    }
+    double sv, cv;
+    sincos((double)m * q.phi[p], &sv, &cv);
+    e = make_double2(r * cv, r * sv);
+  }
+  q.E[(size_t)m * q.npad + p] = e;
+}
+
 // grid: (ncta_p, n_mtiles, nbatch)
 __global__ void __launch_bounds__(PT_NT, 2) points_contract_kernel(const PointParams q) {
   extern __shared__ double acc_s[];   // [PT_PAIRS][2][pitch]
@@ -121,52 +150,41 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_kernel(const PointPa
   if (has_a) {
     for (long long b = batch0; b < batch1; ++b) {
       const long long pbase = b * PT_BATCH + g * PT_PER_LANE;
-      double x[PT_PER_LANE], ph[PT_PER_LANE], u[PT_PER_LANE];
+      double x[PT_PER_LANE];
 #pragma unroll
-      for (int i = 0; i < PT_PER_LANE; ++i) {
-        const long long p = pbase + i;        // npad is a multiple of PT_BATCH
-        x[i] = q.xg[p];
-        ph[i] = (p < q.npts) ? q.phi[p] : 0.0;
-        double uu = sqrt(1.0 - x[i] * x[i]);
-        u[i] = (uu == 0.0) ? 2.220446049250313e-16 : uu;
-      }
+      for (int i = 0; i < PT_PER_LANE; ++i) x[i] = q.xg[pbase + i];      // npad is a multiple of PT_BATCH
       int step = 0;
       for (int which = 0; which < 2; ++which) {
         if (which == 1 && !has_b) break;
         const int m = which ? mb : ma;
-        // per (point, order): e^{i m phi} (:186-188) with the u^m/1e-280 rescale of the scaled
-        // Holmes-Featherstone column folded in, and the two recursion seeds
+        // per (point, order) trig/rescale factors from the precomputed table, and the recursion seeds
         double cm[PT_PER_LANE], sm[PT_PER_LANE], p1[PT_PER_LANE], p2[PT_PER_LANE];
         const double pmm = q.pmm[m], sqm = q.sq[m];
+        const double2* Em = q.E + (size_t)m * q.npad + pbase;
 #pragma unroll
         for (int i = 0; i < PT_PER_LANE; ++i) {
-          double sv, cv;
-          sincos((double)m * ph[i], &sv, &cv);
-          double r = (m == 0) ? 1.0 : 1.0e280, bb = u[i];
-          int e = m;
-          while (e) {
-            if (e & 1) r *= bb;
-            bb *= bb;
-            e >>= 1;
-          }
-          cm[i] = r * cv;
-          sm[i] = r * sv;
+          const double2 e = __ldg(Em + i);
+          cm[i] = e.x;
+          sm[i] = e.y;
           p2[i] = pmm;                      // degree m
           p1[i] = (x[i] * sqm) * pmm;       // degree m+1
         }
-        // W rows are fetched one degree ahead
-        const double* Wl = Wt + (size_t)m * q.npad + pbase;
-        double4 wa = *reinterpret_cast<const double4*>(Wl);
-        double4 wb = *reinterpret_cast<const double4*>(Wl + 4);
+        // Degree loop.  W rows and recursion multipliers live in two register sets used on
+        // alternate degrees (loop unrolled by two, no rotation copies, so a load issued right after
+        // a set is used has a full degree of work to land), with L1 prefetches four rows ahead.
         auto emit = [&](const double(&pl)[PT_PER_LANE], const double4& w0, const double4& w1) {
           const double w[PT_PER_LANE] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-          double c = 0.0, s2 = 0.0;
+          // two interleaved partial sums per component keep the FMA chains short
+          double c0 = 0.0, c1 = 0.0, s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int i = 0; i < PT_PER_LANE; ++i) {
-            const double tv = pl[i] * w[i];
-            c = fma(tv, cm[i], c);
-            s2 = fma(tv, sm[i], s2);
+          for (int i = 0; i < PT_PER_LANE; i += 2) {
+            const double t0 = pl[i] * w[i], t1 = pl[i + 1] * w[i + 1];
+            c0 = fma(t0, cm[i], c0);
+            c1 = fma(t1, cm[i + 1], c1);
+            s0 = fma(t0, sm[i], s0);
+            s1 = fma(t1, sm[i + 1], s1);
           }
+          double c = c0 + c1, s2 = s0 + s1;
           // combine the lanes of the group (fixed butterfly order)
 #pragma unroll
           for (int off = PT_GROUPS / 2; off >= 1; off >>= 1) {
@@ -179,40 +197,54 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_kernel(const PointPa
           }
           ++step;
         };
-        auto next_w = [&](int l, double4& w0, double4& w1) {
+        const double* f1 = q.f1 + m;
+        const double* f2 = q.f2 + m;
+        struct RowSet {
+          double4 w0, w1;
+          double a, b;
+        };
+        auto load_row = [&](RowSet& r, int l) {
           const int ln = min(l, L);
           const double* Wn = Wt + (size_t)ln * q.npad + pbase;
-          w0 = *reinterpret_cast<const double4*>(Wn);
-          w1 = *reinterpret_cast<const double4*>(Wn + 4);
+          r.w0 = *reinterpret_cast<const double4*>(Wn);
+          r.w1 = *reinterpret_cast<const double4*>(Wn + 4);
+          r.a = __ldg(f1 + (size_t)ln * q.Mpad);
+          r.b = __ldg(f2 + (size_t)ln * q.Mpad);
+          const double* Wp = Wt + (size_t)min(l + 4, L) * q.npad + pbase;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(Wp));
         };
+        auto recur = [&](double(&pl)[PT_PER_LANE], const RowSet& r) {
+#pragma unroll
+          for (int i = 0; i < PT_PER_LANE; ++i) {
+            pl[i] = fma(x[i] * r.a, p1[i], -(r.b * p2[i]));
+            p2[i] = p1[i];
+            p1[i] = pl[i];
+          }
+        };
+        RowSet ra, rb;
+        load_row(ra, m);
+        load_row(rb, m + 1);
         // degree m
-        double4 wc = wa, wd = wb;
-        next_w(m + 1, wa, wb);
-        emit(p2, wc, wd);
+        emit(p2, ra.w0, ra.w1);
+        load_row(ra, m + 2);
         if (m + 1 <= L) {
           // degree m+1
-          wc = wa;
-          wd = wb;
-          next_w(m + 2, wa, wb);
-          const double* f1 = q.f1 + m;
-          const double* f2 = q.f2 + m;
-          double fa = __ldg(f1 + (size_t)min(m + 2, L) * q.Mpad), fb = __ldg(f2 + (size_t)min(m + 2, L) * q.Mpad);
-          emit(p1, wc, wd);
-          for (int l = m + 2; l <= L; ++l) {
-            const double a = fa, bq = fb;
-            wc = wa;
-            wd = wb;
-            next_w(l + 1, wa, wb);
-            fa = __ldg(f1 + (size_t)min(l + 1, L) * q.Mpad);
-            fb = __ldg(f2 + (size_t)min(l + 1, L) * q.Mpad);
+          emit(p1, rb.w0, rb.w1);
+          load_row(rb, m + 3);
+          int l = m + 2;
+          for (; l + 1 <= L; l += 2) {
             double pl[PT_PER_LANE];
-#pragma unroll
-            for (int i = 0; i < PT_PER_LANE; ++i) {
-              pl[i] = fma(x[i] * a, p1[i], -(bq * p2[i]));
-              p2[i] = p1[i];
-              p1[i] = pl[i];
-            }
-            emit(pl, wc, wd);
+            recur(pl, ra);
+            emit(pl, ra.w0, ra.w1);
+            load_row(ra, l + 2);
+            recur(pl, rb);
+            emit(pl, rb.w0, rb.w1);
+            load_row(rb, l + 3);
+          }
+          if (l <= L) {
+            double pl[PT_PER_LANE];
+            recur(pl, ra);
+            emit(pl, ra.w0, ra.w1);
           }
         }
       }
@@ -281,7 +313,7 @@ namespace {
 struct PointLayout {
   long long npad;
   int Mpad, ncta_p, batches_per_cta, n_mtiles;
-  size_t off_W, off_x, off_df, off_slots, total;
+  size_t off_W, off_x, off_E, off_df, off_slots, total;
 };
 
 PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num_sms) {
@@ -298,6 +330,7 @@ PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num
   auto take = [&](size_t n) { size_t r = o; o += (n + 31) / 32 * 32; return r; };
   y.off_W = take((size_t)nbatch * (lmax + 1) * y.npad);
   y.off_x = take((size_t)y.npad);
+  y.off_E = take(2 * (size_t)(mmax + 1) * y.npad);
   y.off_df = take((size_t)lmax + 1);
   y.off_slots = take((size_t)y.ncta_p * nbatch * 2 * (lmax + 1) * (mmax + 1));
   y.total = o * sizeof(double);
@@ -430,6 +463,7 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
   q.area_denom = 2.0 * 3.141592653589793 * (rad_e * rad_e);
   q.W = ws + y.off_W;
   q.xg = ws + y.off_x;
+  q.E = reinterpret_cast<double2*>(ws + y.off_E);
   q.f1 = tab;
   q.f2 = tab + (size_t)(lmax + 1) * Mpad;
   q.pmm = q.f2 + (size_t)(lmax + 1) * Mpad;
@@ -444,6 +478,10 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
   {
     dim3 grid((unsigned)((y.npad + 127) / 128), nbatch);
     points_weights_kernel<<<grid, 128, 0, st>>>(q);
+    g_launches.fetch_add(1);
+    MHB_CUDA(cudaGetLastError());
+    dim3 tgrid((unsigned)((y.npad + 127) / 128), mmax + 1);
+    points_trig_kernel<<<tgrid, 128, 0, st>>>(q);
     g_launches.fetch_add(1);
     MHB_CUDA(cudaGetLastError());
   }
