@@ -218,7 +218,9 @@ def run_cuda_arm(args):
         raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+                                timeout=datetime.timedelta(seconds=120))
     dev = torch.device('cuda', local)
     L = _lib.lib()
     T = args.fields
@@ -250,10 +252,11 @@ def run_cuda_arm(args):
     if sampler:
         sampler.start()
         sampler.wait_first_row()
-        # keep the GPU under the same load while nvidia-smi takes its first samples
-        for _ in range(20):
-            out = step()
-        torch.cuda.synchronize()
+    # every rank keeps its GPU under the same load while nvidia-smi takes its first samples
+    # (step() contains the collective, so all ranks must run the same number of steps)
+    for _ in range(20):
+        out = step()
+    torch.cuda.synchronize()
     L.mhb200_profile_enable(1)
     n0 = L.mhb200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
