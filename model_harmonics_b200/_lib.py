@@ -48,6 +48,10 @@ PROTOTYPES = {
                                                       ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, ctypes.c_int,
                                                       ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_float,
                                                       _vp, _vp, _vp]),
+    'mhb200_schedule_probe': (ctypes.c_int, [ctypes.c_int] * 11 + [ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                                              ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                                              ctypes.POINTER(ctypes.c_int)]),
+    'mhb200_fold_probe': (ctypes.c_int, [ctypes.c_int, _c_double_p, ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 5),
     'mhb200_points_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'mhb200_point_pressure_f64': (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64,
                                                  _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,

@@ -894,8 +894,9 @@ struct mhb200_plan {
   int device, nlat, nlon, lmax, mmax;
   int nlb, nmb, Mpad, ntiles, num_sms;
   Variant var[2];
-  double *f1, *f2, *pmm, *sq, *rescale, *x, *w;
-  double* ckpt;            // Legendre restart states (nlb > 1)
+  double *f1 = nullptr, *f2 = nullptr, *pmm = nullptr, *sq = nullptr, *rescale = nullptr, *x = nullptr,
+         *w = nullptr;
+  double* ckpt = nullptr;  // Legendre restart states (nlb > 1)
   // longitude mirror folding: contraction column i pairs grid column colp[i] with its mirror
   // colq[i] (phi_q = -phi_p mod 2 pi; colq == colp for a self-mirrored column)
   bool fold = false;
@@ -909,12 +910,12 @@ struct mhb200_plan {
   cudaEvent_t done_ev = nullptr;
   double* out_dev = nullptr;      // 2 x (lmax+1)(mmax+1)
   double* out_pinned = nullptr;
-  int* lb_first_tile_dev;
+  int* lb_first_tile_dev = nullptr;
   std::vector<int> lb_first_tile;
   // per-call staging (field scales, long degree-factor vectors), grown on demand
-  double* stage_dev;
-  size_t stage_doubles;
-  size_t stage_reserved;   // doubles at the front of the staging buffer used by field scales
+  double* stage_dev = nullptr;
+  size_t stage_doubles = 0;
+  size_t stage_reserved = 0;   // doubles at the front of the staging buffer used by field scales
   std::mutex mu;
 };
 
@@ -951,27 +952,35 @@ int build_schedule(mhb200_plan* pl, Variant& v, int nbatch, int nlev, int mode) 
   return build_schedule_range(pl, v, v.sched, nbatch, nlev, mode, 0, pl->nlat);
 }
 
-// schedule over the rings [h0, h1) only
-int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, int nlev, int mode, int h0,
-                         int h1) {
-  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode && sc.h0 == h0 && sc.h1 == h1) return MHB200_OK;
-  free_schedule(sc);
+// Pure host part of the scheduler (no CUDA): see build_schedule_range.  Exposed to the CPU tests
+// through mhb200_schedule_probe.
+struct HostSchedule {
+  std::vector<Segment> segs;
+  std::vector<int> cta_begin, tile_slot_begin;
+  int ncta = 0;
+};
+
+HostSchedule make_schedule(int nlb, int nmb, int nchunks, int max_ctas, bool fold, int nbatch, int nlev, int mode,
+                           int h0, int h1) {
+  HostSchedule hs;
   struct Tile { int lb, mb; double c; };
   std::vector<Tile> tiles;
-  for (int lb = 0; lb < pl->nlb; ++lb)
-    for (int mb = 0; mb <= std::min(lb, pl->nmb - 1); ++mb)
-      tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev, pl->fold)});
+  for (int lb = 0; lb < nlb; ++lb)
+    for (int mb = 0; mb <= std::min(lb, nmb - 1); ++mb)
+      tiles.push_back({lb, mb, ring_cost(lb == mb, mode, nlev, fold)});
   // per-unit cost = per-ring cost / nchunks (only ratios matter)
-  const long long units_per_tile = (long long)(h1 - h0) * v.nchunks;
-  const long long unit0 = (long long)h0 * v.nchunks;
+  const long long units_per_tile = (long long)(h1 - h0) * nchunks;
+  const long long unit0 = (long long)h0 * nchunks;
   double per_field = 0.0;
   for (auto& tl : tiles) per_field += tl.c * units_per_tile;
   const double total = per_field * nbatch;
   const long long units = (long long)nbatch * (long long)tiles.size() * units_per_tile;
-  const int ncta = (int)std::min<long long>((long long)pl->num_sms * v.ctas_per_sm, units);
-  std::vector<Segment> segs;
-  std::vector<int> cta_begin(ncta + 1, 0);
-  std::vector<int> tile_slot_begin((size_t)nbatch * tiles.size() + 1, 0);
+  const int ncta = (int)std::min<long long>(max_ctas, units);
+  std::vector<Segment>& segs = hs.segs;
+  std::vector<int>& cta_begin = hs.cta_begin;
+  std::vector<int>& tile_slot_begin = hs.tile_slot_begin;
+  cta_begin.assign(ncta + 1, 0);
+  tile_slot_begin.assign((size_t)nbatch * tiles.size() + 1, 0);
   double done = 0.0;
   int cta = 0;
   for (int t = 0; t < nbatch; ++t) {
@@ -1004,12 +1013,23 @@ int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, 
   }
   for (int c = cta + 1; c <= ncta; ++c) cta_begin[c] = (int)segs.size();
   tile_slot_begin.back() = (int)segs.size();
-  sc.ncta = ncta;
-  sc.nseg = (int)segs.size();
+  hs.ncta = ncta;
+  return hs;
+}
+
+// schedule over the rings [h0, h1) only
+int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, int nlev, int mode, int h0,
+                         int h1) {
+  if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode && sc.h0 == h0 && sc.h1 == h1) return MHB200_OK;
+  free_schedule(sc);
+  const HostSchedule hs = make_schedule(pl->nlb, pl->nmb, v.nchunks, pl->num_sms * v.ctas_per_sm, pl->fold, nbatch,
+                                        nlev, mode, h0, h1);
+  sc.ncta = hs.ncta;
+  sc.nseg = (int)hs.segs.size();
   int rc;
-  if ((rc = upload(&sc.segs_dev, segs)) != MHB200_OK) return rc;
-  if ((rc = upload(&sc.cta_seg_begin_dev, cta_begin)) != MHB200_OK) return rc;
-  if ((rc = upload(&sc.tile_slot_begin_dev, tile_slot_begin)) != MHB200_OK) return rc;
+  if ((rc = upload(&sc.segs_dev, hs.segs)) != MHB200_OK) return rc;
+  if ((rc = upload(&sc.cta_seg_begin_dev, hs.cta_begin)) != MHB200_OK) return rc;
+  if ((rc = upload(&sc.tile_slot_begin_dev, hs.tile_slot_begin)) != MHB200_OK) return rc;
   sc.nbatch = nbatch;
   sc.nlev = nlev;
   sc.mode = mode;
@@ -1136,8 +1156,8 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
 // cos(m phi) is shared by the pair and sin(m phi) flips sign, and the Fourier contraction runs over
 // half the columns.  The match must be exact to a few ulp of 2 pi: the fold assumes
 // cos(m phi_q) == cos(m phi_p), and a mismatch delta costs m*delta.
-void find_mirrors(mhb200_plan* pl, const double* phi) {
-  const int n = pl->nlon;
+// pure host: returns whether the grid folds and fills the contraction-column pairs
+bool pair_longitudes(int n, const double* phi, std::vector<int>& colp, std::vector<int>& colq) {
   const double two_pi = 6.283185307179586;
   const double tol = 4.0 * 8.9e-16;
   std::vector<int> mirror(n, -1);
@@ -1172,21 +1192,42 @@ void find_mirrors(mhb200_plan* pl, const double* phi) {
   for (int p = 0; p < n && ok; ++p)
     if (mirror[mirror[p]] != p) ok = false;
   if (getenv("MHB200_NO_FOLD")) ok = false;
-  pl->fold = ok;
-  pl->colp.clear();
-  pl->colq.clear();
+  colp.clear();
+  colq.clear();
   if (ok) {
     std::vector<char> used(n, 0);
     for (int p = 0; p < n; ++p) {
       if (used[p]) continue;
       used[p] = used[mirror[p]] = 1;
-      pl->colp.push_back(p);
-      pl->colq.push_back(mirror[p]);
+      colp.push_back(p);
+      colq.push_back(mirror[p]);
     }
   } else {
     for (int p = 0; p < n; ++p) {
-      pl->colp.push_back(p);
-      pl->colq.push_back(-1);
+      colp.push_back(p);
+      colq.push_back(-1);
+    }
+  }
+  return ok;
+}
+
+void find_mirrors(mhb200_plan* pl, const double* phi) {
+  pl->fold = pair_longitudes(pl->nlon, phi, pl->colp, pl->colq);
+}
+
+// pure host: chunk count and contraction columns per chunk for nf contraction columns
+void choose_chunking(int nf, int kcf_max, int& nchunks, int& kcf) {
+  // the smallest number of chunks, or up to two more when that wastes less padding
+  const int nmin = (nf + kcf_max - 1) / kcf_max;
+  long long best_pad = -1;
+  for (int nc = nmin; nc <= nmin + 2; ++nc) {
+    const int k = (((nf + nc - 1) / nc) + 7) / 8 * 8;
+    if (k > kcf_max) continue;
+    const long long pad = (long long)nc * k;
+    if (best_pad < 0 || pad < best_pad) {
+      best_pad = pad;
+      nchunks = nc;
+      kcf = k;
     }
   }
 }
@@ -1198,19 +1239,7 @@ int build_variant(mhb200_plan* pl, Variant& v, int nth, const double* phi) {
   v.ctas_per_sm = 256 / nth;
   const int nf = (int)pl->colp.size();                 // contraction columns
   const int kcf_max = pl->fold ? nth / 4 : nth / 2;
-  // number of chunks: the smallest, or up to two more when that wastes less padding
-  const int nmin = (nf + kcf_max - 1) / kcf_max;
-  long long best_pad = -1;
-  for (int nc = nmin; nc <= nmin + 2; ++nc) {
-    const int k = (((nf + nc - 1) / nc) + 7) / 8 * 8;
-    if (k > kcf_max) continue;
-    const long long pad = (long long)nc * k;
-    if (best_pad < 0 || pad < best_pad) {
-      best_pad = pad;
-      v.nchunks = nc;
-      v.kcf = k;
-    }
-  }
+  choose_chunking(nf, kcf_max, v.nchunks, v.kcf);
   v.kc = pl->fold ? 2 * v.kcf : v.kcf;
   const int nksc = v.kcf / 4;
   v.nks_total = v.nchunks * nksc;
@@ -1269,9 +1298,13 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   pl->stage_dev = nullptr;
   pl->stage_doubles = 0;
   pl->stage_reserved = 0;
-  cudaDeviceProp prop;
-  MHB_CUDA(cudaGetDeviceProperties(&prop, device));
-  pl->num_sms = prop.multiProcessorCount;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) {
+    set_err("mhb200_plan_create: cannot query the SM count of device %d", device);
+    delete pl;
+    return MHB200_ECUDA;
+  }
+  pl->num_sms = sms;
   pl->lb_first_tile.resize(pl->nlb);
   int nt = 0;
   for (int lb = 0; lb < pl->nlb; ++lb) {
@@ -1281,8 +1314,14 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   pl->ntiles = nt;
 
   find_mirrors(pl, phi);
-  if ((rc = build_variant(pl, pl->var[0], 256, phi)) != MHB200_OK) { delete pl; return rc; }
-  if (pl->nlb == 1 && (rc = build_variant(pl, pl->var[1], 128, phi)) != MHB200_OK) { delete pl; return rc; }
+  if ((rc = build_variant(pl, pl->var[0], 256, phi)) != MHB200_OK) {
+    mhb200_plan_destroy(pl);
+    return rc;
+  }
+  if (pl->nlb == 1 && (rc = build_variant(pl, pl->var[1], 128, phi)) != MHB200_OK) {
+    mhb200_plan_destroy(pl);
+    return rc;
+  }
 
   // Holmes-Featherstone multipliers [(lmax+1)][Mpad], sectoral seeds and sqrt(2m+3)
   const int Mpad = pl->Mpad;
@@ -1324,7 +1363,7 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   if ((rc = upload(&pl->f1, f1)) || (rc = upload(&pl->f2, f2)) || (rc = upload(&pl->pmm, pmm)) ||
       (rc = upload(&pl->sq, sq)) || (rc = upload(&pl->rescale, rescale)) || (rc = upload(&pl->x, xs)) ||
       (rc = upload(&pl->w, ws)) || (rc = upload(&pl->lb_first_tile_dev, pl->lb_first_tile))) {
-    delete pl;
+    mhb200_plan_destroy(pl);
     return rc;
   }
   pl->ckpt = nullptr;
@@ -1602,6 +1641,47 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
   memcpy(clm_host, pl->out_pinned, nout * sizeof(double));
   memcpy(slm_host, pl->out_pinned + nout, nout * sizeof(double));
   return MHB200_OK;
+}
+
+
+// ---- CPU-testable probes of the pure host logic (no CUDA calls)
+// Static schedule for a problem shape: fills seg[5*i..] = (t, lb, mb, u0, u1) and cta_begin[0..ncta];
+// returns the number of segments (or -1 if the buffers are too small); *ncta_out = CTAs used.
+int mhb200_schedule_probe(int nlat, int nchunks, int nlb, int nmb, int nbatch, int max_ctas, int mode, int nlev,
+                          int fold, int h0, int h1, int* seg, int max_segs, int* cta_begin, int max_ctas_buf,
+                          int* ncta_out) {
+  if (nlat < 1 || nchunks < 1 || nlb < 1 || nmb < 1 || nbatch < 1 || max_ctas < 1 || h0 < 0 || h1 > nlat ||
+      h0 >= h1 || !seg || !cta_begin || !ncta_out)
+    return -1;
+  const HostSchedule hs = make_schedule(nlb, nmb, nchunks, max_ctas, fold != 0, nbatch, nlev, mode, h0, h1);
+  if ((int)hs.segs.size() > max_segs || hs.ncta + 1 > max_ctas_buf) return -1;
+  for (size_t i = 0; i < hs.segs.size(); ++i) {
+    seg[5 * i + 0] = hs.segs[i].t;
+    seg[5 * i + 1] = hs.segs[i].lb;
+    seg[5 * i + 2] = hs.segs[i].mb;
+    seg[5 * i + 3] = hs.segs[i].u0;
+    seg[5 * i + 4] = hs.segs[i].u1;
+  }
+  for (int c = 0; c <= hs.ncta; ++c) cta_begin[c] = hs.cta_begin[c];
+  *ncta_out = hs.ncta;
+  return (int)hs.segs.size();
+}
+
+// Longitude pairing and chunking for a CTA shape: fills colp/colq (nlon entries at most) and
+// returns the number of contraction columns; *fold_out, *nchunks_out, *kcf_out describe the layout.
+int mhb200_fold_probe(int nlon, const double* phi, int nth, int* colp, int* colq, int* fold_out, int* nchunks_out,
+                      int* kcf_out) {
+  if (nlon < 1 || !phi || !colp || !colq || !fold_out || !nchunks_out || !kcf_out || (nth != 128 && nth != 256))
+    return -1;
+  std::vector<int> p, q;
+  const bool fold = pair_longitudes(nlon, phi, p, q);
+  for (size_t i = 0; i < p.size(); ++i) {
+    colp[i] = p[i];
+    colq[i] = q[i];
+  }
+  *fold_out = fold ? 1 : 0;
+  choose_chunking((int)p.size(), fold ? nth / 4 : nth / 2, *nchunks_out, *kcf_out);
+  return (int)p.size();
 }
 
 }  // extern "C"

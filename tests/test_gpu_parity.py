@@ -160,3 +160,32 @@ def test_host_band_pipeline_matches_device_path():
     A = mh.gen_atmosphere_stokes(gm, dP[:, :, ::1], *args[2:], **kwargs)
     B = mh.gen_atmosphere_stokes(GPH, dP, *args[2:], **kwargs)
     assert np.array_equal(A.clm, B.clm) and np.array_equal(A.slm, B.slm)
+
+
+@pytest.mark.parametrize('name', ['pressure_options', 'pressure_mean_field', 'pressure_c1'])
+def test_condition_aware_bound_and_truth(name):
+    """
+    Secondary gate: |delta_lm| <= 1e-12 * A_lm per coefficient, A_lm = the sum of the
+    absolute values of the terms of that coefficient.  Informational: literal per-coefficient
+    relative error of the CUDA path and of the reference against an extended-precision evaluation.
+    """
+    from oracle import error_scale as es, stokes_oracle
+    mh = _ops()
+    func, args, kwargs = golden_cases.build(name)
+    A = es.pressure_error_scale(*args, **kwargs)
+    tc, ts = es.pressure_truth(*args, **kwargs)
+    tc, ts = tc.astype(np.float64), ts.astype(np.float64)
+    Y = mh.gen_pressure_stokes(*args, **kwargs)
+    O = stokes_oracle.gen_pressure_stokes(*args, **kwargs)
+    ok = A > 0
+    for got, ref in ((Y.clm, O.clm), (Y.slm, O.slm)):
+        assert np.all(np.abs(got - ref)[ok] <= 1e-12 * A[ok])
+    nz = ok & (np.abs(tc) > 0)
+    lit_gpu = (np.abs(Y.clm - tc)[nz] / np.abs(tc[nz])).max()
+    lit_ref = (np.abs(O.clm - tc)[nz] / np.abs(tc[nz])).max()
+    cond_gpu = (np.abs(Y.clm - tc)[ok] / A[ok]).max()
+    cond_ref = (np.abs(O.clm - tc)[ok] / A[ok]).max()
+    print('%s: vs extended-precision truth -- |d|/A: cuda %.2e, reference %.2e; literal per-coefficient: '
+          'cuda %.2e, reference %.2e' % (name, cond_gpu, cond_ref, lit_gpu, lit_ref))
+    # the CUDA path is as close to the truth as the reference is (within a small factor)
+    assert cond_gpu <= max(4.0 * cond_ref, 1e-14)

@@ -71,3 +71,15 @@ def test_reference_grid_vs_point_consistency():
         assert np.all(np.abs(a.amplitude - b.amplitude) < eps)
         # the two formulations agree to the disc-load approximation, not to rounding
         assert rel_to_max(a.clm, a.slm, b.clm, b.slm) < 1e-3
+
+
+def test_oracle_error_floor_against_extended_precision():
+    """The reference arithmetic itself sits ~1e-16 (relative to A_lm) from an 80-bit evaluation."""
+    from oracle import error_scale as es
+    func, args, kwargs = golden_cases.build('pressure_options')
+    A = es.pressure_error_scale(*args, **kwargs)
+    tc, ts = es.pressure_truth(*args, **kwargs)
+    Y = stokes_oracle.gen_pressure_stokes(*args, **kwargs)
+    ok = A > 0
+    assert (np.abs(Y.clm - tc.astype(np.float64))[ok] / A[ok]).max() < 1e-14
+    assert (np.abs(Y.slm - ts.astype(np.float64))[ok] / A[ok]).max() < 1e-14
