@@ -172,14 +172,15 @@ int mhb200_geopotential_levels_f32(int device, const float* T, const float* Q, c
  * mhb200_schedule_probe: the static equal-cost schedule for a problem shape.  seg receives
  *   5 ints per segment (field, degree block, order block, first unit, end unit), cta_begin the
  *   first segment of every CTA (ncta+1 entries); returns the segment count or -1.
- * mhb200_fold_probe: longitude mirror pairing (colq[i] == colp[i] for a self-mirrored column, -1
- *   when the grid does not fold) and the chunking chosen for a CTA shape (nth = 128 or 256);
- *   returns the number of contraction columns or -1.
+ * mhb200_fold_probe: longitude symmetry pairing and the chunking chosen for a CTA shape (nth = 128
+ *   or 256).  sets receives 4 ints per contraction column: the grid columns at phi, -phi, pi - phi,
+ *   pi + phi (-1 where the fold level does not define them; repeated entries mean a self-paired
+ *   column); *fold_out = 0, 1 or 2; returns the number of contraction columns or -1.
  */
 int mhb200_schedule_probe(int nlat, int nchunks, int nlb, int nmb, int nbatch, int max_ctas, int mode,
                           int nlev, int fold, int h0, int h1, int* seg, int max_segs,
                           int* cta_begin, int max_ctas_buf, int* ncta_out);
-int mhb200_fold_probe(int nlon, const double* phi, int nth, int* colp, int* colq, int* fold_out,
+int mhb200_fold_probe(int nlon, const double* phi, int nth, int* sets, int* unused, int* fold_out,
                       int* nchunks_out, int* kcf_out);
 
 /* counters for bench.py: kernels launched by this library since load (all threads) */

@@ -37,11 +37,11 @@ namespace mhb {
 constexpr int LBLK = 64;          // degrees per block
 constexpr int MBLK = 64;          // orders per block
 constexpr int PLM_PITCH = 65;
-constexpr int CS_ROWS = 36;       // per-thread accumulators kept in shared memory
+constexpr int CS_ROWS = 40;       // per-thread accumulators kept in shared memory (10 sub-tiles x cos,sin x 2)
 constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
 constexpr int DF_MAX = 448;
 constexpr int MAX_PARTS = 16;
-constexpr int LEV_GROUP = 40;     // levels staged per geometry pass
+constexpr int LEV_GROUP = 38;     // levels staged per geometry pass
 
 // CTA shape.  NTH threads handle chunks of up to NTH/2 longitudes.  NTH = 256 runs one CTA per
 // SM; NTH = 128 runs two, so that one CTA's produce phase overlaps the other's contraction
@@ -67,9 +67,10 @@ struct Segment {
 
 struct GridParams {
   int nlat, nlon, lmax, mmax, Mpad, kc, nchunks, nks_total;
-  // longitude mirror folding (see build_variant): kc thread columns per chunk hold kcf folded
-  // columns -- first half the columns p, second half their mirrors q (phi_q = -phi_p mod 2 pi);
-  // unfolded: kcf == kc.  phys[chunk*kc + col] is the grid column of a thread column, or -1.
+  // longitude folding (see build_variant): the kc thread columns of a chunk are nsub = 1, 2 or 4
+  // sub-blocks of kcf contraction columns: the columns p, their mirrors q (phi -> -phi), and, at
+  // fold level 2, p' (phi -> pi - phi) and q'.  phys[chunk*kc + col] is the grid column of a thread
+  // column, or -1.  half_off = doubles per sub-buffer of the chunk buffer.
   int kcf, half_off, fold;
   const int* phys;
   const double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
@@ -231,7 +232,7 @@ __device__ __forceinline__ int bs_index(int l_local, int col) {
 // slot of (degree, thread column) in the chunk buffer: folded chunks keep the columns p in the
 // first half-buffer and their mirrors in the second, both fragment-major over the folded index
 __device__ __forceinline__ int b_slot(const GridParams& p, int l_local, int col) {
-  const int hf = (col >= p.kcf) ? 1 : 0;
+  const int hf = (col >= p.kcf) + (col >= 2 * p.kcf) + (col >= 3 * p.kcf);
   return hf * p.half_off + bs_index(l_local, col - hf * p.kcf);
 }
 
@@ -240,11 +241,26 @@ __device__ __forceinline__ int b_slot(const GridParams& p, int l_local, int col)
 // over half as many columns (cos is even and sin odd under phi -> -phi).
 template <int NTH>
 __device__ __forceinline__ void fold_chunk(const GridParams& p, double* Bs) {
-  const int n = (p.kcf >> 2) * 256;          // doubles per half-buffer
-  for (int i = threadIdx.x; i < n; i += NTH) {
-    const double a = Bs[i], b = Bs[i + p.half_off];
-    Bs[i] = a + b;
-    Bs[i + p.half_off] = a - b;
+  const int n = (p.kcf >> 2) * 256;          // doubles per sub-buffer
+  const int o = p.half_off;
+  if (p.fold == 1) {
+    for (int i = threadIdx.x; i < n; i += NTH) {
+      const double a = Bs[i], b = Bs[i + o];
+      Bs[i] = a + b;
+      Bs[i + o] = a - b;
+    }
+  } else {
+    // level 2: with X1..X4 the chunk values at phi, -phi, pi-phi, pi+phi,
+    //   cos(m phi) terms: (X1+X2) + (-1)^m (X3+X4)      sin(m phi) terms: (X1-X2) - (-1)^m (X3-X4)
+    // sub-buffers after the fold: 0 = even-order cosine, 1 = even-order sine, 2 = odd cosine, 3 = odd sine
+    for (int i = threadIdx.x; i < n; i += NTH) {
+      const double x1 = Bs[i], x2 = Bs[i + o], x3 = Bs[i + 2 * o], x4 = Bs[i + 3 * o];
+      const double s12 = x1 + x2, d12 = x1 - x2, s34 = x3 + x4, d34 = x3 - x4;
+      Bs[i] = s12 + s34;
+      Bs[i + o] = d12 - d34;
+      Bs[i + 2 * o] = s12 - s34;
+      Bs[i + 3 * o] = d12 + d34;
+    }
   }
 }
 
@@ -270,49 +286,76 @@ __device__ __forceinline__ PressureCell load_pressure_cell(const GridParams& p, 
   return c;
 }
 
-// Folded chunks: four threads per folded column (16 degrees each) handle BOTH grid columns p and q
-// and store B_p + B_q / B_p - B_q directly -- no separate fold pass, and 16-step product chains.
-struct PressureCell2 {
-  PressureCell p, q;
+// Folded chunks: four threads per contraction column (16 degrees each) handle all NS = 2 or 4 grid
+// columns of the column's mirror set and store the folded combinations directly -- no separate
+// fold pass, and 16-step product chains.
+template <int NS>
+struct PressureCells {
+  PressureCell c[NS];
 };
-template <int NTH>
-__device__ __forceinline__ PressureCell2 load_pressure_cell2(const GridParams& p, int t, int h, int chunk) {
+template <int NTH, int NS>
+__device__ __forceinline__ PressureCells<NS> load_pressure_cells(const GridParams& p, int t, int h, int chunk) {
   const int j = threadIdx.x % (NTH / 4);
-  PressureCell2 c;
-  c.p.P = c.q.P = 0.0;
-  c.p.G = c.q.G = 1.0;
-  c.p.R = c.q.R = p.rad_e;
+  PressureCells<NS> out;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    out.c[s].P = 0.0;
+    out.c[s].G = 1.0;
+    out.c[s].R = p.rad_e;
+  }
   if (j < p.kcf && h < p.nlat && chunk < p.nchunks) {
-    const int pc = __ldg(p.phys + chunk * p.kc + j), qc = __ldg(p.phys + chunk * p.kc + p.kcf + j);
-    if (pc >= 0) {
-      c.p.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]);
-      c.p.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]);
-      c.p.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]);
-    }
-    if (qc >= 0) {
-      c.q.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + qc * p.Ps[2]);
-      c.q.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + qc * p.Gs[2]);
-      c.q.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + qc * p.Rs[2]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int pc = __ldg(p.phys + chunk * p.kc + s * p.kcf + j);
+      if (pc >= 0) {
+        out.c[s].P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]);
+        out.c[s].G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]);
+        out.c[s].R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]);
+      }
     }
   }
-  return c;
+  return out;
 }
-template <int NTH>
-__device__ __forceinline__ void produce_pressure_folded(const GridParams& p, const PressureCell2& c, int lb,
+// fold level 2 reads its four cells at produce time; this pulls them into L1 one unit ahead
+template <int NTH, int NS>
+__device__ __forceinline__ void prefetch_pressure_cells(const GridParams& p, int t, int h, int chunk) {
+  const int j = threadIdx.x % (NTH / 4), s = threadIdx.x / (NTH / 4);      // one sub-block per thread quarter
+  if (s >= NS || j >= p.kcf || h >= p.nlat || chunk >= p.nchunks) return;
+  const int pc = __ldg(p.phys + chunk * p.kc + s * p.kcf + j);
+  if (pc < 0) return;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]));
+}
+
+template <int NTH, int NS>
+__device__ __forceinline__ void produce_pressure_folded(const GridParams& p, const PressureCells<NS>& cells, int lb,
                                                         double* Bs) {
   const int j = threadIdx.x % (NTH / 4), quarter = threadIdx.x / (NTH / 4);
   if (j >= p.kcf) return;
-  const double fp = c.p.P / c.p.G, rp = c.p.R / p.rad_e;
-  const double fq = c.q.P / c.q.G, rq = c.q.R / p.rad_e;
   const int l0 = 16 * quarter;
-  double vp = fp * ipow(rp, lb * LBLK + l0 + 2), vq = fq * ipow(rq, lb * LBLK + l0 + 2);
-#pragma unroll 8
+  double v[NS], r[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    r[s] = cells.c[s].R / p.rad_e;
+    v[s] = (cells.c[s].P / cells.c[s].G) * ipow(r[s], lb * LBLK + l0 + 2);
+  }
+  const int o = p.half_off;
+#pragma unroll 4
   for (int i = 0; i < 16; ++i) {
     const int slot = bs_index(l0 + i, j);
-    Bs[slot] = vp + vq;
-    Bs[slot + p.half_off] = vp - vq;
-    vp *= rp;
-    vq *= rq;
+    if (NS == 2) {
+      Bs[slot] = v[0] + v[1];
+      Bs[slot + o] = v[0] - v[1];
+    } else {
+      const double s12 = v[0] + v[1], d12 = v[0] - v[1], s34 = v[2] + v[3], d34 = v[2] - v[3];
+      Bs[slot] = s12 + s34;
+      Bs[slot + o] = d12 - d34;
+      Bs[slot + 2 * o] = s12 - s34;
+      Bs[slot + 3 * o] = d12 + d34;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) v[s] *= r[s];
   }
 }
 
@@ -638,41 +681,50 @@ __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h
 // ---------------------------------------------------------------------------------------
 // One segment: work units [u0, u1) (unit = ring * nchunks + chunk) of tile (lb, mb) of field t.
 //
-// DIAG tile (lb == mb): only the 8x8 sub-tiles with degree-tile >= order-tile are needed (36 of
-// 64).  Order groups are paired (g, 7-g): 9 (order-group, degree-tile) sub-tiles per pair,
-// balanced.  Warp w takes pair w & 3; with 8 warps the two warps of a pair split the k-steps
-// by parity (w >> 2), with 4 warps each warp takes every k-step.
-// FULL tile (8 warps only): warp w owns order group w and all 8 degree tiles.
+// Order groups.  The 64 orders of a tile are split by parity and then into groups of 8:
+// group (par, gi), gi = 0..3, holds the orders 16*gi + 2*r + par, r = 0..7 (row tile
+// (par*4 + gi)*2 + {cos, sin} of the trig table).  Keeping a parity per row tile is what lets
+// fold level 2 give even and odd orders different right-hand sides.
+// DIAG tile (lb == mb): group gi only needs the degree tiles lt >= 2*gi (8 - 2*gi of them).  The
+// groups gi and 3 - gi of one parity are paired: 10 (group, degree-tile) sub-tiles per pair, four
+// pairs.  Warp w takes pair w & 3; with 8 warps the two warps of a pair split the k-steps by
+// parity (w >> 2), with 4 warps each warp takes every k-step.
+// FULL tile (8 warps only): warp w owns group (w >> 2, w & 3) and all 8 degree tiles.
 // ---------------------------------------------------------------------------------------
 template <int MODE, typename Tin, bool DIAG, int NTH>
 __device__ __forceinline__ void run_segment(const GridParams& p, const Segment seg, int slot_index,
                                             double* Bs, double* Cs, double* plm_s) {
   constexpr int NW = Shape<NTH>::NW;
   static_assert(DIAG || NW == 8, "FULL tiles need the 8-warp shape");
-  constexpr int NP = DIAG ? 9 : 8;               // accumulator pairs per thread
+  constexpr int NP = DIAG ? 10 : 8;              // accumulator pairs per thread
   constexpr int NA = DIAG ? 4 : 2;               // trig fragments per k-step
   constexpr int KSTRIDE = (DIAG && NW == 8) ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = (DIAG && NW == 8) ? (warp >> 2) : 0;
-  const int gA = DIAG ? (warp & 3) : warp;
-  const int gB = DIAG ? (7 - gA) : warp;
-  const int nA = DIAG ? (8 - gA) : 8;
+  // order parity and group indices (within the parity) of this warp
+  const int par = DIAG ? ((warp & 3) >> 1) : (warp >> 2);
+  const int gA = DIAG ? (warp & 1) : (warp & 3);
+  const int gB = DIAG ? (3 - gA) : gA;
+  const int nA = DIAG ? (8 - 2 * gA) : 8;        // sub-tiles of group gA; the rest belong to gB
+  const int rtA = (par * 4 + gA) * 2, rtB = (par * 4 + gB) * 2;     // cosine row tiles (sine = +1)
   const int nksc = p.kcf >> 2;        // contraction k-steps per chunk
 
   int lt[NP];          // degree tile of pair j
 #pragma unroll
-  for (int j = 0; j < NP; ++j) lt[j] = DIAG ? ((j < nA) ? (gA + j) : (j - 1)) : j;
+  for (int j = 0; j < NP; ++j) lt[j] = DIAG ? ((j < nA) ? (2 * gA + j) : (j - 2)) : j;
 
 #pragma unroll
   for (int i = 0; i < NP * 4; ++i) Cs[i * NTH + tid] = 0.0;
 
   const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
   PressureCell cell;
-  PressureCell2 cell2;
+  PressureCells<2> cell2;
   const bool pfold = (MODE == MODE_PRESSURE) && p.fold;
   if (MODE == MODE_PRESSURE) {
-    if (pfold) cell2 = load_pressure_cell2<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
-    else cell = load_pressure_cell<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+    // (fold level 2 loads its four cells at produce time: holding them across the contraction
+    // would cost 24 registers)
+    if (p.fold == 1) cell2 = load_pressure_cells<NTH, 2>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+    else if (p.fold == 0) cell = load_pressure_cell<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
   }
   for (int h = hfirst; h <= hlast; ++h) {
     // chunks of this ring that belong to the segment (partial rings are fine: the Legendre
@@ -687,8 +739,12 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
     for (int chunk = cbeg; chunk < cend; ++chunk) {
       if (MODE == MODE_PRESSURE) {
-        if (pfold) produce_pressure_folded<NTH>(p, cell2, seg.lb, Bs);
-        else produce_pressure<NTH>(p, cell, seg.lb, Bs);
+        if (p.fold == 2)
+          produce_pressure_folded<NTH, 4>(p, load_pressure_cells<NTH, 4>(p, seg.t, h, chunk), seg.lb, Bs);
+        else if (p.fold == 1)
+          produce_pressure_folded<NTH, 2>(p, cell2, seg.lb, Bs);
+        else
+          produce_pressure<NTH>(p, cell, seg.lb, Bs);
       } else {
         produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs);
       }
@@ -700,7 +756,8 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
       if (MODE == MODE_PRESSURE) {
         // the next unit's cells are fetched now, so their DRAM/L2 latency hides behind the contraction
         const bool last = (chunk + 1 == p.nchunks);
-        if (pfold) cell2 = load_pressure_cell2<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        if (p.fold == 2) prefetch_pressure_cells<NTH, 4>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        else if (p.fold == 1) cell2 = load_pressure_cells<NTH, 2>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
         else cell = load_pressure_cell<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }
 
@@ -718,23 +775,25 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
       const int klast = nksc - 1;
       auto load_a = [&](double(&a)[NA], int k) {
         const double* ap = Ablk + (size_t)min(k, klast) * 512;
-        a[0] = __ldg(ap + (gA * 2) * 32);
-        a[1] = __ldg(ap + (gA * 2 + 1) * 32);
+        a[0] = __ldg(ap + rtA * 32);
+        a[1] = __ldg(ap + (rtA + 1) * 32);
         if (DIAG) {
-          a[2] = __ldg(ap + (gB * 2) * 32);
-          a[3] = __ldg(ap + (gB * 2 + 1) * 32);
+          a[2] = __ldg(ap + rtB * 32);
+          a[3] = __ldg(ap + (rtB + 1) * 32);
         }
       };
-      // B fragments: cosine rows contract with the first half-buffer (B_p + B_q when folded), sine
-      // rows with the second (B_p - B_q); unfolded chunks have a single buffer (half_off = 0)
+      // B fragments.  Unfolded: one buffer for everything.  Fold level 1: cosine rows contract with
+      // sub-buffer 0 (B_p + B_q), sine rows with sub-buffer 1 (B_p - B_q).  Level 2: even orders use
+      // sub-buffers 0 / 1, odd orders 2 / 3 (see fold_chunk).
       const int brot = lane >> 2, bcol = lane & 3;
-      const double* Bsin = Bs + (p.fold ? p.half_off : 0);
+      const double* Bcos = Bs + ((p.fold == 2 && par) ? 2 * p.half_off : 0);
+      const double* Bsin = Bs + ((p.fold == 2) ? (par ? 3 : 1) * p.half_off : (p.fold == 1 ? p.half_off : 0));
       auto mma_step = [&](const double(&c)[NA], int k) {
         const int boff = k * 256 + (((brot + k) & 7) << 2) + bcol;
         double bc[NP], bs[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          bc[j] = Bs[boff + lt[j] * 32];
+          bc[j] = Bcos[boff + lt[j] * 32];
           bs[j] = Bsin[boff + lt[j] * 32];
         }
 #pragma unroll
@@ -771,7 +830,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const int g = ((!DIAG) || (j < nA)) ? gA : gB;
-      const int m_local = g * 8 + (lane >> 2);
+      const int m_local = 16 * g + 2 * (lane >> 2) + par;
       const int l_local = lt[j] * 8 + 2 * (lane & 3);
       const double w0 = plm_s[m_local * PLM_PITCH + l_local];
       const double w1 = plm_s[m_local * PLM_PITCH + l_local + 1];
@@ -791,7 +850,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const int g = ((!DIAG) || (j < nA)) ? gA : gB;
-      const int m_local = g * 8 + (lane >> 2);
+      const int m_local = 16 * g + 2 * (lane >> 2) + par;
       const int l_local = lt[j] * 8 + 2 * (lane & 3);
 #pragma unroll
       for (int cs = 0; cs < 2; ++cs) {
@@ -899,8 +958,8 @@ struct mhb200_plan {
   double* ckpt = nullptr;  // Legendre restart states (nlb > 1)
   // longitude mirror folding: contraction column i pairs grid column colp[i] with its mirror
   // colq[i] (phi_q = -phi_p mod 2 pi; colq == colp for a self-mirrored column)
-  bool fold = false;
-  std::vector<int> colp, colq;
+  int fold = 0;            // 0: none, 1: phi -> -phi, 2: also phi -> pi - phi
+  std::vector<int> colp, colq, colp2, colq2;
   // host-pipelined atmosphere path: per-band schedules, device cubes, copy stream
   Schedule band_sched[MAX_PARTS];
   void* cube_dev[2] = {nullptr, nullptr};
@@ -929,8 +988,9 @@ int upload(T** dev, const std::vector<T>& host) {
 }
 
 // fp64-pipe cost (arbitrary units per longitude) of one ring of one tile
-double ring_cost(bool diag, int mode, int nlev, bool fold) {
-  const double mma = (diag ? 4608.0 : 8192.0) * (fold ? 0.5 : 1.0);
+double ring_cost(bool diag, int mode, int nlev, int fold) {
+  // contraction slots per grid column: 10 of 16 (diagonal) or 16 of 16 sub-tile pairs, x cos/sin, x 256/...
+  const double mma = (diag ? 5120.0 : 8192.0) / (double)(1 << fold);
   const double prod = (mode == MODE_PRESSURE) ? 90.0 : (double)nlev * 136.0;
   return mma + prod;
 }
@@ -960,7 +1020,7 @@ struct HostSchedule {
   int ncta = 0;
 };
 
-HostSchedule make_schedule(int nlb, int nmb, int nchunks, int max_ctas, bool fold, int nbatch, int nlev, int mode,
+HostSchedule make_schedule(int nlb, int nmb, int nchunks, int max_ctas, int fold, int nbatch, int nlev, int mode,
                            int h0, int h1) {
   HostSchedule hs;
   struct Tile { int lb, mb; double c; };
@@ -1132,7 +1192,7 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
   gp.Mpad = pl->Mpad;
   gp.kc = v.kc;
   gp.kcf = v.kcf;
-  gp.fold = pl->fold ? 1 : 0;
+  gp.fold = pl->fold;
   gp.half_off = pl->fold ? (v.kcf / 4) * 256 : 0;
   gp.phys = v.phys;
   gp.nchunks = v.nchunks;
@@ -1152,15 +1212,17 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
 }
 
 // trig table, fragment-major [mb][kstep][16 row tiles][32 lanes]  (m_phi, gen_pressure_stokes.py:176-177)
-// Pairs every longitude with its mirror (phi_q = -phi_p mod 2 pi).  Regular grids have one; then
-// cos(m phi) is shared by the pair and sin(m phi) flips sign, and the Fourier contraction runs over
-// half the columns.  The match must be exact to a few ulp of 2 pi: the fold assumes
-// cos(m phi_q) == cos(m phi_p), and a mismatch delta costs m*delta.
-// pure host: returns whether the grid folds and fills the contraction-column pairs
-bool pair_longitudes(int n, const double* phi, std::vector<int>& colp, std::vector<int>& colq) {
+// Longitude symmetries of the grid.  Level 1 pairs every longitude with its mirror
+// (phi_q = -phi_p mod 2 pi): cos(m phi) is shared by the pair and sin(m phi) flips sign, so the
+// Fourier contraction runs over half the columns.  Level 2 additionally pairs phi with pi - phi:
+// cos(m (pi - phi)) = (-1)^m cos(m phi), sin(m (pi - phi)) = -(-1)^m sin(m phi), a quarter of the
+// columns with separate right-hand sides for even and odd orders.  Regular grids with an even
+// number of longitudes have both.  A match must be exact to a few ulp of 2 pi: the folds assume
+// equal trig values, and a mismatch delta costs m*delta.
+static bool involution(int n, const double* phi, double offset, std::vector<int>& partner) {
   const double two_pi = 6.283185307179586;
   const double tol = 4.0 * 8.9e-16;
-  std::vector<int> mirror(n, -1);
+  partner.assign(n, -1);
   std::vector<std::pair<double, int>> key(n);
   for (int p = 0; p < n; ++p) {
     double a = fmod(phi[p], two_pi);
@@ -1168,9 +1230,8 @@ bool pair_longitudes(int n, const double* phi, std::vector<int>& colp, std::vect
     key[p] = {a, p};
   }
   std::sort(key.begin(), key.end());
-  bool ok = true;
-  for (int p = 0; p < n && ok; ++p) {
-    double want = fmod(-phi[p], two_pi);
+  for (int p = 0; p < n; ++p) {
+    double want = fmod(offset - phi[p], two_pi);
     if (want < 0) want += two_pi;
     // nearest key (also across the 0 / 2 pi seam)
     auto it = std::lower_bound(key.begin(), key.end(), std::make_pair(want, -1));
@@ -1186,33 +1247,64 @@ bool pair_longitudes(int n, const double* phi, std::vector<int>& colp, std::vect
         best = key[idx].second;
       }
     }
-    if (best < 0 || bestd > tol) ok = false;
-    else mirror[p] = best;
+    if (best < 0 || bestd > tol) return false;
+    partner[p] = best;
   }
-  for (int p = 0; p < n && ok; ++p)
-    if (mirror[mirror[p]] != p) ok = false;
-  if (getenv("MHB200_NO_FOLD")) ok = false;
+  for (int p = 0; p < n; ++p)
+    if (partner[partner[p]] != p) return false;
+  return true;
+}
+
+// pure host: fold level of the grid and the contraction-column sets (colq/colp2/colq2 are -1 where
+// the level does not define them; equal entries mean a self-paired column)
+int pair_longitudes(int n, const double* phi, std::vector<int>& colp, std::vector<int>& colq,
+                    std::vector<int>& colp2, std::vector<int>& colq2) {
+  std::vector<int> m1, m2;
+  int level = 0;
+  if (involution(n, phi, 0.0, m1)) {
+    level = 1;
+    if (involution(n, phi, 3.141592653589793, m2)) {
+      level = 2;
+      // the two symmetries must commute on the grid (they do for any consistent rounding)
+      for (int p = 0; p < n; ++p)
+        if (m1[m2[p]] != m2[m1[p]]) level = 1;
+    }
+  }
+  if (getenv("MHB200_NO_FOLD")) level = 0;
+  if (const char* e = getenv("MHB200_FOLD")) level = std::min(level, std::max(0, atoi(e)));
   colp.clear();
   colq.clear();
-  if (ok) {
-    std::vector<char> used(n, 0);
-    for (int p = 0; p < n; ++p) {
-      if (used[p]) continue;
-      used[p] = used[mirror[p]] = 1;
-      colp.push_back(p);
-      colq.push_back(mirror[p]);
-    }
-  } else {
-    for (int p = 0; p < n; ++p) {
-      colp.push_back(p);
+  colp2.clear();
+  colq2.clear();
+  std::vector<char> used(n, 0);
+  for (int p = 0; p < n; ++p) {
+    if (used[p]) continue;
+    colp.push_back(p);
+    used[p] = 1;
+    if (level == 0) {
       colq.push_back(-1);
+      colp2.push_back(-1);
+      colq2.push_back(-1);
+      continue;
     }
+    const int q = m1[p];
+    used[q] = 1;
+    colq.push_back(q);
+    if (level == 1) {
+      colp2.push_back(-1);
+      colq2.push_back(-1);
+      continue;
+    }
+    const int p2 = m2[p], q2 = m1[p2];
+    used[p2] = used[q2] = 1;
+    colp2.push_back(p2);
+    colq2.push_back(q2);
   }
-  return ok;
+  return level;
 }
 
 void find_mirrors(mhb200_plan* pl, const double* phi) {
-  pl->fold = pair_longitudes(pl->nlon, phi, pl->colp, pl->colq);
+  pl->fold = pair_longitudes(pl->nlon, phi, pl->colp, pl->colq, pl->colp2, pl->colq2);
 }
 
 // pure host: chunk count and contraction columns per chunk for nf contraction columns
@@ -1238,35 +1330,40 @@ int build_variant(mhb200_plan* pl, Variant& v, int nth, const double* phi) {
   v.nth = nth;
   v.ctas_per_sm = 256 / nth;
   const int nf = (int)pl->colp.size();                 // contraction columns
-  const int kcf_max = pl->fold ? nth / 4 : nth / 2;
+  const int nsub = 1 << pl->fold;                      // grid columns per contraction column
+  const int kcf_max = (nth / 2) / nsub;
   choose_chunking(nf, kcf_max, v.nchunks, v.kcf);
-  v.kc = pl->fold ? 2 * v.kcf : v.kcf;
+  v.kc = nsub * v.kcf;
   const int nksc = v.kcf / 4;
   v.nks_total = v.nchunks * nksc;
+  const std::vector<int>* sets[4] = {&pl->colp, &pl->colq, &pl->colp2, &pl->colq2};
   std::vector<int> phys((size_t)v.nchunks * v.kc, -1);
   for (int c = 0; c < v.nchunks; ++c)
     for (int j = 0; j < v.kcf; ++j) {
       const int idx = c * v.kcf + j;
       if (idx >= nf) continue;
-      phys[(size_t)c * v.kc + j] = pl->colp[idx];
-      if (pl->fold) phys[(size_t)c * v.kc + v.kcf + j] = pl->colq[idx];
+      for (int sb = 0; sb < nsub; ++sb) phys[(size_t)c * v.kc + sb * v.kcf + j] = (*sets[sb])[idx];
     }
+  // row tile (par*4 + gi)*2 + {cos, sin}, row r: order 16*gi + 2*r + par of the block (see run_segment)
   std::vector<double> trig((size_t)pl->nmb * v.nks_total * 512, 0.0);
   for (int mb = 0; mb < pl->nmb; ++mb)
     for (int ks = 0; ks < v.nks_total; ++ks)
       for (int g = 0; g < 8; ++g)
         for (int lane = 0; lane < 32; ++lane) {
-          const int m = mb * MBLK + g * 8 + (lane >> 2);
+          const int par = g >> 2, gi = g & 3;
+          const int m = mb * MBLK + 16 * gi + 2 * (lane >> 2) + par;
           const int c = ks / nksc, jloc = (ks % nksc) * 4 + (lane & 3);
           const int idx = c * v.kcf + jloc;
           if (m > pl->mmax || idx >= nf) continue;
           const int p = pl->colp[idx];
-          // a self-mirrored column appears in both half-buffers: halve it (its sine part cancels)
-          const double wc = (pl->fold && pl->colq[idx] == p) ? 0.5 : 1.0;
+          // a self-paired column appears twice among its sub-blocks: halve it
+          double wgt = 1.0;
+          if (pl->fold >= 1 && pl->colq[idx] == p) wgt = 0.5;
+          if (pl->fold >= 2 && pl->colp2[idx] == p) wgt = 0.5;
           const double arg = (double)m * phi[p];
           const size_t base = (((size_t)mb * v.nks_total + ks) * 16 + g * 2) * 32 + lane;
-          trig[base] = wc * cos(arg);
-          trig[base + 32] = sin(arg);
+          trig[base] = wgt * cos(arg);
+          trig[base + 32] = wgt * sin(arg);
         }
   int rc = upload(&v.trig, trig);
   if (rc != MHB200_OK) return rc;
@@ -1653,7 +1750,7 @@ int mhb200_schedule_probe(int nlat, int nchunks, int nlb, int nmb, int nbatch, i
   if (nlat < 1 || nchunks < 1 || nlb < 1 || nmb < 1 || nbatch < 1 || max_ctas < 1 || h0 < 0 || h1 > nlat ||
       h0 >= h1 || !seg || !cta_begin || !ncta_out)
     return -1;
-  const HostSchedule hs = make_schedule(nlb, nmb, nchunks, max_ctas, fold != 0, nbatch, nlev, mode, h0, h1);
+  const HostSchedule hs = make_schedule(nlb, nmb, nchunks, max_ctas, fold, nbatch, nlev, mode, h0, h1);
   if ((int)hs.segs.size() > max_segs || hs.ncta + 1 > max_ctas_buf) return -1;
   for (size_t i = 0; i < hs.segs.size(); ++i) {
     seg[5 * i + 0] = hs.segs[i].t;
@@ -1673,14 +1770,17 @@ int mhb200_fold_probe(int nlon, const double* phi, int nth, int* colp, int* colq
                       int* kcf_out) {
   if (nlon < 1 || !phi || !colp || !colq || !fold_out || !nchunks_out || !kcf_out || (nth != 128 && nth != 256))
     return -1;
-  std::vector<int> p, q;
-  const bool fold = pair_longitudes(nlon, phi, p, q);
+  std::vector<int> p, q, p2, q2;
+  const int fold = pair_longitudes(nlon, phi, p, q, p2, q2);
   for (size_t i = 0; i < p.size(); ++i) {
-    colp[i] = p[i];
-    colq[i] = q[i];
+    colp[4 * i + 0] = p[i];
+    colp[4 * i + 1] = q[i];
+    colp[4 * i + 2] = p2[i];
+    colp[4 * i + 3] = q2[i];
   }
-  *fold_out = fold ? 1 : 0;
-  choose_chunking((int)p.size(), fold ? nth / 4 : nth / 2, *nchunks_out, *kcf_out);
+  (void)colq;
+  *fold_out = fold;
+  choose_chunking((int)p.size(), (nth / 2) >> fold, *nchunks_out, *kcf_out);
   return (int)p.size();
 }
 

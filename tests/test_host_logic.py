@@ -54,7 +54,7 @@ def test_schedule_covers_every_unit_once_and_balances(shape):
     # equal-cost split: per-CTA cost within one unit of the mean (cost model of ring_cost)
     mode, nlev, fold = shape.get('mode', 1), shape.get('nlev', 37), shape.get('fold', 1)
     def cost(lb, mb):
-        mma = (4608.0 if lb == mb else 8192.0) * (0.5 if fold else 1.0)
+        mma = (5120.0 if lb == mb else 8192.0) / (1 << fold)
         return mma + (90.0 if mode == 0 else nlev * 136.0)
     per = np.array([sum((s[4] - s[3]) * cost(s[1], s[2]) for s in seg[cta[c]:cta[c + 1]]) for c in range(ncta)])
     if per.sum() > 0 and ncta > 1:
@@ -68,39 +68,71 @@ def _fold(lon_deg, nth, wrap=True):
     if wrap:
         phi = np.where(phi < 0, phi + 2.0 * np.pi, phi)
     n = len(phi)
-    colp = np.zeros(n, dtype=np.int32)
-    colq = np.zeros(n, dtype=np.int32)
+    sets = np.zeros(4 * n, dtype=np.int32)
+    dummy = np.zeros(1, dtype=np.int32)
     fold, nchunks, kcf = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
-    nf = _lib.lib().mhb200_fold_probe(n, _lib.as_double_p(np.ascontiguousarray(phi)), nth, colp.ctypes.data_as(INT_P),
-                                      colq.ctypes.data_as(INT_P), ctypes.byref(fold), ctypes.byref(nchunks),
+    nf = _lib.lib().mhb200_fold_probe(n, _lib.as_double_p(np.ascontiguousarray(phi)), nth, sets.ctypes.data_as(INT_P),
+                                      dummy.ctypes.data_as(INT_P), ctypes.byref(fold), ctypes.byref(nchunks),
                                       ctypes.byref(kcf))
     assert nf > 0
-    return phi, colp[:nf], colq[:nf], fold.value, nchunks.value, kcf.value
+    return phi, sets[:4 * nf].reshape(nf, 4), fold.value, nchunks.value, kcf.value
 
 
-@pytest.mark.parametrize('lon', [np.arange(1440) * 0.25, np.arange(360) * 1.0, -180.0 + np.arange(120) * 3.0,
-                                 np.arange(-179.5, 180.0, 1.0), np.arange(7) * (360.0 / 7), np.arange(90) * 4.0 - 180.0])
+def _folded_sums(phi, sets, fold, B, mmax):
+    """Fourier sums over the contraction columns exactly as the kernel forms them."""
+    dc, ds = np.zeros(mmax + 1), np.zeros(mmax + 1)
+    for p, q, p2, q2 in sets:
+        x1 = B[p]
+        x2 = B[q] if fold >= 1 else 0.0
+        x3 = B[p2] if fold >= 2 else 0.0
+        x4 = B[q2] if fold >= 2 else 0.0
+        w = 1.0
+        if fold >= 1 and q == p:
+            w = 0.5
+        if fold >= 2 and p2 == p:
+            w = 0.5
+        s12, d12, s34, d34 = x1 + x2, x1 - x2, x3 + x4, x3 - x4
+        for m in range(mmax + 1):
+            if fold == 0:
+                bc, bs = x1, x1
+            elif fold == 1:
+                bc, bs = s12, d12
+            else:
+                bc, bs = (s12 + s34, d12 - d34) if m % 2 == 0 else (s12 - s34, d12 + d34)
+            dc[m] += w * np.cos(m * phi[p]) * bc
+            ds[m] += w * np.sin(m * phi[p]) * bs
+    return dc, ds
+
+
+@pytest.mark.parametrize('lon,level', [(np.arange(1440) * 0.25, 2), (np.arange(360) * 1.0, 2),
+                                       (-180.0 + np.arange(120) * 3.0, 2), (np.arange(-179.5, 180.0, 1.0), 2),
+                                       (np.arange(7) * (360.0 / 7), 1), (np.arange(90) * 4.0 - 180.0, 2),
+                                       (np.arange(18) * 20.0, 2), (np.arange(10) * 36.0, 2)])
 @pytest.mark.parametrize('nth', [128, 256])
-def test_regular_grids_fold_into_mirror_pairs(lon, nth):
-    phi, colp, colq, fold, nchunks, kcf = _fold(lon, nth)
+def test_regular_grids_fold_and_reproduce_the_fourier_sums(lon, level, nth):
+    phi, sets, fold, nchunks, kcf = _fold(lon, nth)
     n = len(phi)
-    assert fold == 1
-    # every grid column appears exactly once (self-mirrored ones as their own partner)
+    assert fold == level
+    # every grid column appears in exactly one contraction column
     seen = np.zeros(n, dtype=int)
-    for p, q in zip(colp, colq):
-        seen[p] += 1
-        if q != p:
-            seen[q] += 1
-        # mirror relation: phi_p + phi_q is a multiple of 2 pi to a few ulp
-        d = (phi[p] + phi[q]) / (2.0 * np.pi)
-        assert abs(d - round(d)) < 1e-15
+    for row in sets:
+        for c in set(int(v) for v in row[:1 << fold]):
+            seen[c] += 1
     assert np.all(seen == 1)
-    # chunking holds all contraction columns with little padding and fits the CTA shape
-    assert kcf % 8 == 0 and kcf <= nth // 4 and nchunks * kcf >= len(colp)
-    assert nchunks * kcf - len(colp) < max(0.08 * len(colp), 8 * nchunks)
+    # the folded sums equal the direct ones
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal(n)
+    mmax = 40
+    dc, ds = _folded_sums(phi, sets, fold, B, mmax)
+    m = np.arange(mmax + 1)[:, None]
+    want_c, want_s = np.cos(m * phi[None, :]) @ B, np.sin(m * phi[None, :]) @ B
+    scale = np.abs(want_c).max()
+    assert np.abs(dc - want_c).max() <= 1e-12 * scale and np.abs(ds - want_s).max() <= 1e-12 * scale
+    # chunking holds all contraction columns and fits the CTA shape
+    assert kcf % 8 == 0 and kcf <= (nth // 2) >> fold and nchunks * kcf >= len(sets)
 
 
 def test_asymmetric_grid_does_not_fold():
-    phi, colp, colq, fold, nchunks, kcf = _fold(np.arange(90) * 4.0 + 0.7, 256)
-    assert fold == 0 and np.all(colq == -1) and np.array_equal(colp, np.arange(90))
+    phi, sets, fold, nchunks, kcf = _fold(np.arange(90) * 4.0 + 0.7, 256)
+    assert fold == 0 and np.all(sets[:, 1:] == -1) and np.array_equal(sets[:, 0], np.arange(90))
     assert kcf <= 128 and nchunks * kcf >= 90
