@@ -359,6 +359,59 @@ __device__ __forceinline__ void produce_pressure_folded(const GridParams& p, con
   }
 }
 
+// Fold level 2, pressure mode, in two balanced stages.  Stage A: one thread per grid cell of the
+// chunk (4 sub-blocks x kcf) loads P, G, R and stages (f r^(64 lb + 2), r), f = P/G, r = R/rad_e
+// -- the divisions and the long power are done once per cell.  Stage B: every thread takes one
+// contraction column and 8 of the 64 degrees, jumps to its first degree with a short power and
+// writes the four folded combinations (see fold_chunk) with 8-step product chains.
+template <int NTH>
+__device__ __forceinline__ void produce_pressure_fold2(const GridParams& p, int t, int h, int lb, int chunk,
+                                                       double* Bs) {
+  constexpr int JW = NTH / 8;                       // contraction columns a chunk can hold at level 2
+  double2* stg = reinterpret_cast<double2*>(Bs + 4 * p.half_off);      // [4][kcf], past the four sub-buffers
+  const int tid = threadIdx.x;
+  if (tid < 4 * p.kcf) {
+    const int pc = __ldg(p.phys + chunk * p.kc + tid);                // thread columns are [sub-block][j]
+    double v = 0.0, r = 1.0;
+    if (pc >= 0) {
+      const double Pv = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]);
+      const double Gv = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]);
+      const double Rv = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]);
+      r = Rv / p.rad_e;
+      v = (Pv / Gv) * ipow(r, lb * LBLK + 2);
+    }
+    stg[tid] = make_double2(v, r);
+  }
+  __syncthreads();
+  const int j = tid % JW, part = tid / JW;
+  if (j >= p.kcf) return;
+  const int l0 = 8 * part, o = p.half_off;
+  double v[4], r[4];
+#pragma unroll
+  for (int sb = 0; sb < 4; ++sb) {
+    const double2 e = stg[sb * p.kcf + j];
+    r[sb] = e.y;
+    // r^(8 part), part = 0..7, from three squarings
+    const double r2 = e.y * e.y, r4 = r2 * r2, r8 = r4 * r4;
+    double pw = (part & 1) ? r8 : 1.0;
+    const double r16 = r8 * r8;
+    if (part & 2) pw *= r16;
+    if (part & 4) pw *= r16 * r16;
+    v[sb] = e.x * pw;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int slot = bs_index(l0 + i, j);
+    const double s12 = v[0] + v[1], d12 = v[0] - v[1], s34 = v[2] + v[3], d34 = v[2] - v[3];
+    Bs[slot] = s12 + s34;
+    Bs[slot + o] = d12 - d34;
+    Bs[slot + 2 * o] = s12 - s34;
+    Bs[slot + 3 * o] = d12 + d34;
+#pragma unroll
+    for (int sb = 0; sb < 4; ++sb) v[sb] *= r[sb];
+  }
+}
+
 template <int NTH>
 __device__ __forceinline__ void produce_pressure(const GridParams& p, const PressureCell& cell, int lb, double* Bs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -740,7 +793,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
     for (int chunk = cbeg; chunk < cend; ++chunk) {
       if (MODE == MODE_PRESSURE) {
         if (p.fold == 2)
-          produce_pressure_folded<NTH, 4>(p, load_pressure_cells<NTH, 4>(p, seg.t, h, chunk), seg.lb, Bs);
+          produce_pressure_fold2<NTH>(p, seg.t, h, seg.lb, chunk, Bs);
         else if (p.fold == 1)
           produce_pressure_folded<NTH, 2>(p, cell2, seg.lb, Bs);
         else
