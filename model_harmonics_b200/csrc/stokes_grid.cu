@@ -712,22 +712,30 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 // contraction phase so that DRAM latency is off the critical path)
 template <typename Tin, int NTH>
 __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
-  if (h >= p.nlat || chunk >= p.nchunks) return;
-  const int col = threadIdx.x;
-  if (col >= p.kc) return;
+  if (h >= p.nlat || chunk >= p.nchunks) return;      // uniform over the CTA
+  constexpr int KC = Shape<NTH>::KC;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int col = tid & (KC - 1);                     // both halves of the CTA scan the same columns:
+  const int which = tid / KC;                         // the lower half prefetches GPH, the upper half dP
   const int per_line = 128 / (int)sizeof(Tin);
-  const int pc = __ldg(p.phys + chunk * p.kc + col);
-  if (pc < 0) return;
-  // one thread per 128-byte line: the first thread column that falls into it
-  const int prev = (col > 0) ? __ldg(p.phys + chunk * p.kc + col - 1) : -1;
-  if (prev >= 0 && (prev / per_line) == (pc / per_line)) return;
+  int pc = -1, prev = -1;
+  if (col < p.kc) {
+    pc = __ldg(p.phys + chunk * p.kc + col);
+    if (col > 0) prev = __ldg(p.phys + chunk * p.kc + col - 1);
+  }
+  // a 128-byte line is named once, by the first thread column that falls into it; the levels of a
+  // line are then spread over the lanes of the warp (a few prefetches per lane instead of 2*nlev
+  // in a single thread)
+  const bool leader = (pc >= 0) && !(prev >= 0 && (prev / per_line) == (pc / per_line));
+  unsigned mask = __ballot_sync(0xffffffffu, leader);
   const size_t lev_stride = (size_t)p.nlat * p.nlon;
-  const size_t base = (size_t)t * p.batch_stride + (size_t)h * p.nlon + pc;
-  const Tin* g = (const Tin*)p.GPH + base;
-  const Tin* d = (const Tin*)p.dP + base;
-  for (int k = 0; k < p.nlev; ++k) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)k * lev_stride));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)k * lev_stride));
+  const Tin* base = (which ? (const Tin*)p.dP : (const Tin*)p.GPH) + (size_t)t * p.batch_stride + (size_t)h * p.nlon;
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int c = __shfl_sync(0xffffffffu, pc, src);
+    for (int k = lane; k < p.nlev; k += 32)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * lev_stride + c));
   }
 }
 

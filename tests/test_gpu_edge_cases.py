@@ -64,7 +64,7 @@ def test_atmosphere_boundary_sizes(nlev, nlat, nlon, L, M, method):
 
 
 @pytest.mark.parametrize('n,L,M', [(1, 4, None), (31, 0, None), (33, 1, None), (257, 70, None), (100, 100, 64),
-                                    (64, 12, 0)])
+                                    (64, 12, 0), (5000, 130, 101), (20000, 61, 3)])
 def test_points_boundary_sizes(n, L, M):
     from oracle import stokes_oracle
     mh, syn = _mh(), _syn()
