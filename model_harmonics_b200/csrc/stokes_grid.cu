@@ -573,7 +573,7 @@ __device__ __forceinline__ void level_elements(const double (&z)[GW], const doub
 // ---------------------------------------------------------------------------------------
 template <int MODE, typename Tin, int NTH>
 __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, int h, int lb, int chunk,
-                                                   double* Bs) {
+                                                   double* Bs, int known_col) {
   constexpr int KC = Shape<NTH>::KC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* stg = reinterpret_cast<double2*>(Bs);            // [level in group][KC columns]
@@ -586,7 +586,8 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
   }
   // geometry-pass ownership: a fixed column, levels of parity tid / KC
   const int gcol = tid & (KC - 1), gpar = tid / KC;
-  const int gpcol = (gcol < p.kc) ? __ldg(p.phys + chunk * p.kc + gcol) : -1;
+  // known_col: this thread's grid column if the preceding prefetch_chunk already fetched it (>= -1)
+  const int gpcol = (known_col >= -1) ? known_col : ((gcol < p.kc) ? __ldg(p.phys + chunk * p.kc + gcol) : -1);
   const bool gactive = (gpcol >= 0);
   const int gpc = gactive ? gpcol : 0;
   ColumnGeom cg;
@@ -684,7 +685,9 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
         }
       }
     }
-    __syncthreads();
+    // The staged columns of warps w and w + NWH are produced and consumed by exactly those two
+    // warps (same 32 columns in both passes), so the hand-over is a 64-thread named barrier.
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp % NWH)) : "memory");
     // ---- accumulate pass
     if (half) {
 #pragma unroll 2
@@ -710,9 +713,10 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 
 // L2 prefetch of the cube data the next chunk's geometry pass will read (issued before the
 // contraction phase so that DRAM latency is off the critical path)
+// Returns the grid column of this thread's column of that chunk (-1 = none), or -2 if nothing was fetched.
 template <typename Tin, int NTH>
-__device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
-  if (h >= p.nlat || chunk >= p.nchunks) return;      // uniform over the CTA
+__device__ __forceinline__ int prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
+  if (h >= p.nlat || chunk >= p.nchunks) return -2;   // uniform over the CTA
   constexpr int KC = Shape<NTH>::KC;
   const int tid = threadIdx.x, lane = tid & 31;
   const int col = tid & (KC - 1);                     // both halves of the CTA scan the same columns:
@@ -737,6 +741,7 @@ __device__ __forceinline__ void prefetch_chunk(const GridParams& p, int t, int h
     for (int k = lane; k < p.nlev; k += 32)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * lev_stride + c));
   }
+  return pc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -778,6 +783,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
   for (int i = 0; i < NP * 4; ++i) Cs[i * NTH + tid] = 0.0;
 
   const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
+  int next_col = -2;          // grid column of this thread in the next chunk once prefetch_chunk has read it
   PressureCell cell;
   PressureCells<2> cell2;
   const bool pfold = (MODE == MODE_PRESSURE) && p.fold;
@@ -807,7 +813,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
         else
           produce_pressure<NTH>(p, cell, seg.lb, Bs);
       } else {
-        produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs);
+        produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs, next_col);
       }
       __syncthreads();
       if (p.fold && !pfold) {
@@ -825,7 +831,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
       if (MODE != MODE_PRESSURE) {
         // start pulling the next chunk's (or next ring's first chunk's) cube data into L2
         const bool last = (chunk + 1 == p.nchunks);
-        prefetch_chunk<Tin, NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        next_col = prefetch_chunk<Tin, NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }
       // contraction over the chunk's longitudes; trig fragments straight from L2 (fragment-major
       // table: one coalesced 256-byte load per fragment, prefetched three k-steps ahead in a
