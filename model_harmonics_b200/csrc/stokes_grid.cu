@@ -436,12 +436,17 @@ __device__ __forceinline__ void produce_pressure(const GridParams& p, const Pres
 // statement at a time across the W independent elements, so that the instruction stream
 // itself carries the ILP needed to cover the 8-cycle DFMA latency at 2 warps per scheduler.
 constexpr int GW = 4;
+// Newton steps after the hardware seed (relative error <= 8.8e-7 measured) and before the final
+// residual correction.  One step already gives the correctly rounded quotient / root on 2^30 random
+// operands in the geometry pass's ranges and <= 1 ulp on wide-range operands
+// (bench_micro/newton_check.cu, profiles/r01_newton_check.jsonl); it was 3.
+constexpr int NEWTON_STEPS = 1;
 
 __device__ __forceinline__ void rcp_w(const double (&a)[GW], double (&y)[GW]) {
 #pragma unroll
   for (int i = 0; i < GW; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(a[i]));
 #pragma unroll
-  for (int it = 0; it < 3; ++it) {
+  for (int it = 0; it < NEWTON_STEPS; ++it) {
     double e[GW];
 #pragma unroll
     for (int i = 0; i < GW; ++i) e[i] = fma(-a[i], y[i], 1.0);
@@ -470,7 +475,7 @@ __device__ __forceinline__ void sqrt_w(const double (&a)[GW], double (&g)[GW]) {
     h[i] = 0.5 * y;
   }
 #pragma unroll
-  for (int it = 0; it < 3; ++it) {
+  for (int it = 0; it < NEWTON_STEPS; ++it) {
 #pragma unroll
     for (int i = 0; i < GW; ++i) r[i] = fma(-g[i], h[i], 0.5);
 #pragma unroll
