@@ -55,7 +55,8 @@ struct Shape {
   // pairs of the atmosphere geometry pass (LEV_GROUP x KC x 16 B)
   static constexpr int REGION0 = LEV_GROUP * KC * 2;
   static_assert(REGION0 >= KS * 256, "region 0 must hold the B chunk");
-  static constexpr size_t SMEM = (size_t)(REGION0 + CS_ROWS * NTH + MBLK * PLM_PITCH) * sizeof(double);
+  // + 16 doubles: the colatitude-only factors of the atmosphere geometry for this ring and the next
+  static constexpr size_t SMEM = (size_t)(REGION0 + CS_ROWS * NTH + MBLK * PLM_PITCH + 16) * sizeof(double);
 };
 
 enum Mode { MODE_PRESSURE = 0, MODE_ATM_BC05 = 1, MODE_ATM_SW02 = 2 };
@@ -516,6 +517,14 @@ __device__ __forceinline__ void accumulate_level(double (&acc)[32], double u, do
   }
 }
 
+// what prefetch_chunk already fetched for this thread's column of the next chunk: grid column
+// (-1 none, -2 nothing fetched) and its geoid / longitude factors, so that the produce phase starts
+// without a dependent chain of global loads
+struct NextCol {
+  int pc;
+  double geo, cphi, sphi;
+};
+
 // per-column / per-ring constants of the atmosphere geometry
 struct ColumnGeom {
   double NG, NG1, cphi, sphi, geo_over;
@@ -578,7 +587,7 @@ __device__ __forceinline__ void level_elements(const double (&z)[GW], const doub
 // ---------------------------------------------------------------------------------------
 template <int MODE, typename Tin, int NTH>
 __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, int h, int lb, int chunk,
-                                                   double* Bs, int known_col) {
+                                                   double* Bs, const NextCol& nx, const double* ring_s) {
   constexpr int KC = Shape<NTH>::KC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double2* stg = reinterpret_cast<double2*>(Bs);            // [level in group][KC columns]
@@ -591,24 +600,25 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
   }
   // geometry-pass ownership: a fixed column, levels of parity tid / KC
   const int gcol = tid & (KC - 1), gpar = tid / KC;
-  // known_col: this thread's grid column if the preceding prefetch_chunk already fetched it (>= -1)
-  const int gpcol = (known_col >= -1) ? known_col : ((gcol < p.kc) ? __ldg(p.phys + chunk * p.kc + gcol) : -1);
+  const bool known = (nx.pc >= -1);
+  const int gpcol = known ? nx.pc : ((gcol < p.kc) ? __ldg(p.phys + chunk * p.kc + gcol) : -1);
   const bool gactive = (gpcol >= 0);
   const int gpc = gactive ? gpcol : 0;
   ColumnGeom cg;
   {
-    // ring (colatitude-only) factors built on the host; geoid per column
-    const double geo = (p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + gpc * p.geo_s1) : 0.0;
-    cg.a1 = p.ring_tab[0 * p.nlat + h];
-    cg.a2 = p.ring_tab[1 * p.nlat + h];
-    cg.NG = p.ring_tab[2 * p.nlat + h] + geo;     // (N + GEOID)
-    cg.NG1 = p.ring_tab[3 * p.nlat + h] + geo;    // (N(1-e^2) + GEOID)
-    cg.st = p.ring_tab[4 * p.nlat + h];
-    cg.ct = p.ring_tab[5 * p.nlat + h];
-    cg.gs = p.ring_tab[6 * p.nlat + h];
-    cg.c1 = p.ring_tab[7 * p.nlat + h];
-    cg.cphi = p.lon_tab[gpc];
-    cg.sphi = p.lon_tab[p.nlon + gpc];
+    // ring (colatitude-only) factors built on the host (cached in shared memory); geoid per column
+    const double geo = known ? nx.geo : ((p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + gpc * p.geo_s1) : 0.0);
+    const double* rs = ring_s + (h & 1) * 8;
+    cg.a1 = rs[0];
+    cg.a2 = rs[1];
+    cg.NG = rs[2] + geo;      // (N + GEOID)
+    cg.NG1 = rs[3] + geo;     // (N(1-e^2) + GEOID)
+    cg.st = rs[4];
+    cg.ct = rs[5];
+    cg.gs = rs[6];
+    cg.c1 = rs[7];
+    cg.cphi = known ? nx.cphi : p.lon_tab[gpc];
+    cg.sphi = known ? nx.sphi : p.lon_tab[p.nlon + gpc];
     cg.rad_e = p.rad_e;
     cg.inv_rad = 1.0 / p.rad_e;
     cg.geo_over = geo / p.rad_e;
@@ -718,10 +728,13 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
 
 // L2 prefetch of the cube data the next chunk's geometry pass will read (issued before the
 // contraction phase so that DRAM latency is off the critical path)
-// Returns the grid column of this thread's column of that chunk (-1 = none), or -2 if nothing was fetched.
+// Also fetches what the produce phase needs first for this thread's column of that chunk (NextCol).
 template <typename Tin, int NTH>
-__device__ __forceinline__ int prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
-  if (h >= p.nlat || chunk >= p.nchunks) return -2;   // uniform over the CTA
+__device__ __forceinline__ NextCol prefetch_chunk(const GridParams& p, int t, int h, int chunk) {
+  NextCol nx;
+  nx.pc = -2;
+  nx.geo = nx.cphi = nx.sphi = 0.0;
+  if (h >= p.nlat || chunk >= p.nchunks) return nx;   // uniform over the CTA
   constexpr int KC = Shape<NTH>::KC;
   const int tid = threadIdx.x, lane = tid & 31;
   const int col = tid & (KC - 1);                     // both halves of the CTA scan the same columns:
@@ -746,7 +759,12 @@ __device__ __forceinline__ int prefetch_chunk(const GridParams& p, int t, int h,
     for (int k = lane; k < p.nlev; k += 32)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * lev_stride + c));
   }
-  return pc;
+  nx.pc = pc;
+  const int gpc = (pc >= 0) ? pc : 0;
+  nx.geo = (p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + gpc * p.geo_s1) : 0.0;
+  nx.cphi = __ldg(p.lon_tab + gpc);
+  nx.sphi = __ldg(p.lon_tab + p.nlon + gpc);
+  return nx;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -788,7 +806,14 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
   for (int i = 0; i < NP * 4; ++i) Cs[i * NTH + tid] = 0.0;
 
   const int hfirst = seg.u0 / p.nchunks, hlast = (seg.u1 - 1) / p.nchunks;
-  int next_col = -2;          // grid column of this thread in the next chunk once prefetch_chunk has read it
+  NextCol next_col;           // this thread's column of the next chunk once prefetch_chunk has read it
+  next_col.pc = -2;
+  next_col.geo = next_col.cphi = next_col.sphi = 0.0;
+  double* ring_s = plm_s + MBLK * PLM_PITCH;
+  if (MODE != MODE_PRESSURE) {
+    if (tid < 8) ring_s[(hfirst & 1) * 8 + tid] = p.ring_tab[tid * p.nlat + hfirst];
+    __syncthreads();
+  }
   PressureCell cell;
   PressureCells<2> cell2;
   const bool pfold = (MODE == MODE_PRESSURE) && p.fold;
@@ -804,6 +829,9 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
     const int cbeg = (h == hfirst) ? (seg.u0 - h * p.nchunks) : 0;
     const int cend = (h == hlast) ? (seg.u1 - h * p.nchunks) : p.nchunks;
     if (tid < MBLK) legendre_ring(p, h, seg.lb, seg.mb, tid, plm_s);
+    // next ring's colatitude factors (visible long before they are needed: every chunk has barriers)
+    if (MODE != MODE_PRESSURE && tid >= MBLK && tid < MBLK + 8 && h < hlast)
+      ring_s[((h + 1) & 1) * 8 + (tid - MBLK)] = p.ring_tab[(tid - MBLK) * p.nlat + h + 1];
 
     double acc[NP][2][2];
 #pragma unroll
@@ -818,7 +846,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
         else
           produce_pressure<NTH>(p, cell, seg.lb, Bs);
       } else {
-        produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs, next_col);
+        produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs, next_col, ring_s);
       }
       __syncthreads();
       if (p.fold && !pfold) {
