@@ -317,16 +317,29 @@ __device__ __forceinline__ PressureCells<NS> load_pressure_cells(const GridParam
   }
   return out;
 }
-// fold level 2 reads its four cells at produce time; this pulls them into L1 one unit ahead
-template <int NTH, int NS>
-__device__ __forceinline__ void prefetch_pressure_cells(const GridParams& p, int t, int h, int chunk) {
-  const int j = threadIdx.x % (NTH / 4), s = threadIdx.x / (NTH / 4);      // one sub-block per thread quarter
-  if (s >= NS || j >= p.kcf || h >= p.nlat || chunk >= p.nchunks) return;
-  const int pc = __ldg(p.phys + chunk * p.kc + s * p.kcf + j);
-  if (pc < 0) return;
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]));
+// fold level 2: thread tid < 4*kcf owns the cell of thread column tid (layout [sub-block][j]) and loads it
+// one unit ahead -- before the contraction, so that the DRAM/L2 latency hides behind it (3 values per
+// thread, unlike the 12 of a thread that owned a contraction column)
+struct CellA {
+  double P, G, R;
+  bool ok;
+};
+template <int NTH>
+__device__ __forceinline__ CellA load_cell_a(const GridParams& p, int t, int h, int chunk) {
+  CellA c;
+  c.P = 0.0;
+  c.G = 1.0;
+  c.R = p.rad_e;
+  c.ok = false;
+  const int tid = threadIdx.x;
+  if (tid >= 4 * p.kcf || h >= p.nlat || chunk >= p.nchunks) return c;
+  const int pc = __ldg(p.phys + chunk * p.kc + tid);
+  if (pc < 0) return c;
+  c.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]);
+  c.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]);
+  c.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]);
+  c.ok = true;
+  return c;
 }
 
 template <int NTH, int NS>
@@ -361,25 +374,20 @@ __device__ __forceinline__ void produce_pressure_folded(const GridParams& p, con
 }
 
 // Fold level 2, pressure mode, in two balanced stages.  Stage A: one thread per grid cell of the
-// chunk (4 sub-blocks x kcf) loads P, G, R and stages (f r^(64 lb + 2), r), f = P/G, r = R/rad_e
+// chunk (4 sub-blocks x kcf) -- which loaded P, G, R one unit ahead (load_cell_a) -- stages (f r^(64 lb + 2), r), f = P/G, r = R/rad_e
 // -- the divisions and the long power are done once per cell.  Stage B: every thread takes one
 // contraction column and 8 of the 64 degrees, jumps to its first degree with a short power and
 // writes the four folded combinations (see fold_chunk) with 8-step product chains.
 template <int NTH>
-__device__ __forceinline__ void produce_pressure_fold2(const GridParams& p, int t, int h, int lb, int chunk,
-                                                       double* Bs) {
+__device__ __forceinline__ void produce_pressure_fold2(const GridParams& p, const CellA& cell, int lb, double* Bs) {
   constexpr int JW = NTH / 8;                       // contraction columns a chunk can hold at level 2
   double2* stg = reinterpret_cast<double2*>(Bs + 4 * p.half_off);      // [4][kcf], past the four sub-buffers
   const int tid = threadIdx.x;
   if (tid < 4 * p.kcf) {
-    const int pc = __ldg(p.phys + chunk * p.kc + tid);                // thread columns are [sub-block][j]
     double v = 0.0, r = 1.0;
-    if (pc >= 0) {
-      const double Pv = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + pc * p.Ps[2]);
-      const double Gv = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + pc * p.Gs[2]);
-      const double Rv = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + pc * p.Rs[2]);
-      r = Rv / p.rad_e;
-      v = (Pv / Gv) * ipow(r, lb * LBLK + 2);
+    if (cell.ok) {
+      r = cell.R / p.rad_e;
+      v = (cell.P / cell.G) * ipow(r, lb * LBLK + 2);
     }
     stg[tid] = make_double2(v, r);
   }
@@ -816,11 +824,11 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
   }
   PressureCell cell;
   PressureCells<2> cell2;
+  CellA cellA;
   const bool pfold = (MODE == MODE_PRESSURE) && p.fold;
   if (MODE == MODE_PRESSURE) {
-    // (fold level 2 loads its four cells at produce time: holding them across the contraction
-    // would cost 24 registers)
-    if (p.fold == 1) cell2 = load_pressure_cells<NTH, 2>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+    if (p.fold == 2) cellA = load_cell_a<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
+    else if (p.fold == 1) cell2 = load_pressure_cells<NTH, 2>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
     else if (p.fold == 0) cell = load_pressure_cell<NTH>(p, seg.t, hfirst, seg.u0 - hfirst * p.nchunks);
   }
   for (int h = hfirst; h <= hlast; ++h) {
@@ -840,7 +848,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
     for (int chunk = cbeg; chunk < cend; ++chunk) {
       if (MODE == MODE_PRESSURE) {
         if (p.fold == 2)
-          produce_pressure_fold2<NTH>(p, seg.t, h, seg.lb, chunk, Bs);
+          produce_pressure_fold2<NTH>(p, cellA, seg.lb, Bs);
         else if (p.fold == 1)
           produce_pressure_folded<NTH, 2>(p, cell2, seg.lb, Bs);
         else
@@ -856,7 +864,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
       if (MODE == MODE_PRESSURE) {
         // the next unit's cells are fetched now, so their DRAM/L2 latency hides behind the contraction
         const bool last = (chunk + 1 == p.nchunks);
-        if (p.fold == 2) prefetch_pressure_cells<NTH, 4>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
+        if (p.fold == 2) cellA = load_cell_a<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
         else if (p.fold == 1) cell2 = load_pressure_cells<NTH, 2>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
         else cell = load_pressure_cell<NTH>(p, seg.t, last ? h + 1 : h, last ? 0 : chunk + 1);
       }

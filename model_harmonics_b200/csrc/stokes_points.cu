@@ -356,22 +356,35 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_staged(const PointPa
   asm volatile("cp.async.commit_group;");
 
   for (int i = tid; i < PT_PAIRS * 2 * pitch; i += PT_NT) acc_s[i] = 0.0;
-  for (int i = tid; i < PT_PAIRS * fpitch; i += PT_NT) {
-    const int pr = i / fpitch, s = i - pr * fpitch;
-    const int a = m0 + pr, bo = m1 - pr, na = L + 1 - a;
-    double2 v = make_double2(0.0, 0.0);               // idle groups, silent second walks, the step past the end: p stays 0
-    if (a <= bo && s < nsteps) {
-      int l = -1, m = 0;
+  // (blocks of 8 entries per thread: the table loads of a block are independent, so their latencies overlap)
+  for (int i0 = tid; i0 < PT_PAIRS * fpitch; i0 += 8 * PT_NT) {
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * PT_NT;
+      const int pr = i / fpitch, s = i - pr * fpitch;
+      const int a = m0 + pr, bo = m1 - pr, na = L + 1 - a;
+      // idle groups, silent second walks, the step past the end: multipliers 0, so p stays 0
+      int l = 0, m = 0;
+      bool live = (i < PT_PAIRS * fpitch) && (a <= bo) && (s < nsteps);
       if (s < na) {
         l = a + s;
         m = a;
       } else if (a < bo) {
         l = bo + (s - na);
         m = bo;
+      } else {
+        live = false;
       }
-      if (l >= 0) v = make_double2(__ldg(q.f1 + (size_t)l * q.Mpad + m), __ldg(q.f2 + (size_t)l * q.Mpad + m));
+      const size_t o = live ? (size_t)l * q.Mpad + m : 0;
+      const double f1v = __ldg(q.f1 + o), f2v = __ldg(q.f2 + o);
+      v[k] = live ? make_double2(f1v, f2v) : make_double2(0.0, 0.0);
     }
-    fab_s[i] = v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * PT_NT;
+      if (i < PT_PAIRS * fpitch) fab_s[i] = v[k];
+    }
   }
   const double pmmA = q.pmm[mA], pmmB = q.pmm[mB];
   const int winc = has_a ? WT_PITCH : 0;              // idle groups stay on one row
@@ -775,7 +788,10 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
     }
     dim3 grid(y.ncta_p, y.n_mtiles, nbatch);
     profile_begin(st);
-    if (smem_staged <= smem_max) {
+    // the staged kernel only where two of its CTAs fit on an SM (each CTA also reserves 1 KB): with
+    // one CTA (4 warps) per SM the direct-load kernel at two CTAs hides its latencies better
+    const size_t smem_two_ctas = (228 * 1024) / 2 - 1024;
+    if (smem_staged <= smem_two_ctas) {
       MHB_CUDA(cudaFuncSetAttribute(points_contract_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_staged));
       points_contract_staged<<<grid, PT_NT, smem_staged, st>>>(q);
