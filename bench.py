@@ -219,6 +219,8 @@ def run_cuda_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         import datetime
+        # stdout carries exactly one JSON line: NCCL's own version / debug lines go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local),
                                 timeout=datetime.timedelta(seconds=120))
     dev = torch.device('cuda', local)
