@@ -119,7 +119,7 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': 'fields/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, cores=None):
@@ -219,8 +219,6 @@ def run_cuda_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         import datetime
-        # stdout carries exactly one JSON line: NCCL's own version / debug lines go to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local),
                                 timeout=datetime.timedelta(seconds=120))
     dev = torch.device('cuda', local)
@@ -391,7 +389,7 @@ def run_cuda_arm(args):
                                 'sample': cpu_sample_description(), 'seconds': wall}
     if world == 1 and not args.no_extra:
         line['other_workloads'] = other_workloads(mh, syn, torch, L)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -458,7 +456,31 @@ def other_workloads(mh, syn, torch, L):
     return out
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything libraries write to file descriptor 1 while the
+    benchmark runs (NCCL prints its version there) goes to stderr; the line is written to the real
+    stdout by emit()."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
