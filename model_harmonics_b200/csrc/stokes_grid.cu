@@ -74,6 +74,10 @@ struct GridParams {
   // column, or -1.  half_off = doubles per sub-buffer of the chunk buffer.
   int kcf, half_off, fold;
   const int* phys;
+  // L2 prefetch lists built by the plan: for chunk c and element size e (0: 8 bytes, 1: 4 bytes),
+  // pf_cols[(2c + e) * kc + i], i < pf_count[2c + e], is the first grid column of the i-th distinct
+  // 128-byte line the chunk's columns fall into
+  const int *pf_cols, *pf_count;
   const double *trig, *f1, *f2, *pmm, *sq, *rescale, *x, *w;
   const double* plm_table;
   const double* ckpt;          // Legendre restart states [nlat][nlb][Mpad][2] (nlb > 1), else null
@@ -744,28 +748,27 @@ __device__ __forceinline__ NextCol prefetch_chunk(const GridParams& p, int t, in
   nx.geo = nx.cphi = nx.sphi = 0.0;
   if (h >= p.nlat || chunk >= p.nchunks) return nx;   // uniform over the CTA
   constexpr int KC = Shape<NTH>::KC;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int col = tid & (KC - 1);                     // both halves of the CTA scan the same columns:
-  const int which = tid / KC;                         // the lower half prefetches GPH, the upper half dP
-  const int per_line = 128 / (int)sizeof(Tin);
-  int pc = -1, prev = -1;
-  if (col < p.kc) {
-    pc = __ldg(p.phys + chunk * p.kc + col);
-    if (col > 0) prev = __ldg(p.phys + chunk * p.kc + col - 1);
-  }
-  // a 128-byte line is named once, by the first thread column that falls into it; the levels of a
-  // line are then spread over the lanes of the warp (a few prefetches per lane instead of 2*nlev
-  // in a single thread)
-  const bool leader = (pc >= 0) && !(prev >= 0 && (prev / per_line) == (pc / per_line));
-  unsigned mask = __ballot_sync(0xffffffffu, leader);
-  const size_t lev_stride = (size_t)p.nlat * p.nlon;
-  const Tin* base = (which ? (const Tin*)p.dP : (const Tin*)p.GPH) + (size_t)t * p.batch_stride + (size_t)h * p.nlon;
-  while (mask) {
-    const int src = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int c = __shfl_sync(0xffffffffu, pc, src);
-    for (int k = lane; k < p.nlev; k += 32)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * lev_stride + c));
+  const int tid = threadIdx.x;
+  const int col = tid & (KC - 1);
+  const int pc = (col < p.kc) ? __ldg(p.phys + chunk * p.kc + col) : -1;
+  // one prefetch per 128-byte line, level and cube, spread over the whole CTA: thread (slot, level
+  // phase) = (tid & 7, tid >> 3) takes the lines slot, slot + 8, ... of the plan's list at the
+  // levels phase, phase + NTH/8, ...
+  {
+    const int e = (sizeof(Tin) == 4) ? 1 : 0;
+    const int n = __ldg(p.pf_count + 2 * chunk + e);
+    const int* list = p.pf_cols + (size_t)(2 * chunk + e) * p.kc;
+    const size_t lev_stride = (size_t)p.nlat * p.nlon;
+    const size_t row = (size_t)t * p.batch_stride + (size_t)h * p.nlon;
+    const Tin* g = (const Tin*)p.GPH + row;
+    const Tin* d = (const Tin*)p.dP + row;
+    for (int i = tid & 7; i < n; i += 8) {
+      const int c = __ldg(list + i);
+      for (int k = tid >> 3; k < p.nlev; k += NTH / 8) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (size_t)k * lev_stride + c));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)k * lev_stride + c));
+      }
+    }
   }
   nx.pc = pc;
   const int gpc = (pc >= 0) ? pc : 0;
@@ -1054,6 +1057,7 @@ struct Variant {
   int kc = 0, kcf = 0, nchunks = 0, nks_total = 0;   // thread columns / contraction columns per chunk
   double* trig = nullptr;
   int* phys = nullptr;                               // [nchunks][kc] grid column of each thread column
+  int *pf_cols = nullptr, *pf_count = nullptr;       // L2 prefetch line lists (GridParams::pf_cols)
   Schedule sched;
 };
 
@@ -1303,6 +1307,8 @@ void fill_plan_params(const mhb200_plan* pl, const Variant& v, GridParams& gp) {
   gp.fold = pl->fold;
   gp.half_off = pl->fold ? (v.kcf / 4) * 256 : 0;
   gp.phys = v.phys;
+  gp.pf_cols = v.pf_cols;
+  gp.pf_count = v.pf_count;
   gp.nchunks = v.nchunks;
   gp.nks_total = v.nks_total;
   gp.trig = v.trig;
@@ -1473,8 +1479,26 @@ int build_variant(mhb200_plan* pl, Variant& v, int nth, const double* phi) {
           trig[base] = wgt * cos(arg);
           trig[base + 32] = wgt * sin(arg);
         }
+  // L2 prefetch lists: first column of every distinct 128-byte line among a chunk's grid columns (in
+  // thread-column order, so that runs stay together), for 8-byte and 4-byte elements
+  std::vector<int> pf_cols((size_t)v.nchunks * 2 * v.kc, 0), pf_count((size_t)v.nchunks * 2, 0);
+  for (int c = 0; c < v.nchunks; ++c)
+    for (int e = 0; e < 2; ++e) {
+      const int per_line = e ? 32 : 16;
+      int n = 0, last_line = -1;
+      for (int col = 0; col < v.kc; ++col) {
+        const int pc = phys[(size_t)c * v.kc + col];
+        if (pc < 0) continue;
+        if (pc / per_line == last_line) continue;
+        last_line = pc / per_line;
+        pf_cols[((size_t)c * 2 + e) * v.kc + n++] = pc;
+      }
+      pf_count[(size_t)c * 2 + e] = n;
+    }
   int rc = upload(&v.trig, trig);
   if (rc != MHB200_OK) return rc;
+  if ((rc = upload(&v.pf_cols, pf_cols)) != MHB200_OK) return rc;
+  if ((rc = upload(&v.pf_count, pf_count)) != MHB200_OK) return rc;
   return upload(&v.phys, phys);
 }
 
@@ -1594,6 +1618,8 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   for (auto& v : pl->var) {
     if (v.trig) cudaFree(v.trig);
     if (v.phys) cudaFree(v.phys);
+    if (v.pf_cols) cudaFree(v.pf_cols);
+    if (v.pf_count) cudaFree(v.pf_count);
     free_schedule(v.sched);
   }
   cudaFree(pl->f1);
