@@ -717,13 +717,13 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
     asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp % NWH)) : "memory");
     // ---- accumulate pass
     if (half) {
-#pragma unroll 2
+#pragma unroll 4
       for (int kk = 0; kk < ng; ++kk) {
         const double2 e = stg[kk * KC + acol];
         accumulate_level<true>(acc, e.x, e.y);
       }
     } else {
-#pragma unroll 2
+#pragma unroll 4
       for (int kk = 0; kk < ng; ++kk) {
         const double2 e = stg[kk * KC + acol];
         accumulate_level<false>(acc, e.x, e.y);
