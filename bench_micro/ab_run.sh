@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-for lib in libmhb200_u4.so libmhb200_u6.so libmhb200_u8.so libmhb200_u4.so; do
-  echo "== $lib"
-  MHB200_LIB=$PWD/model_harmonics_b200/$lib timeout 300 python bench_micro/first_timing.py c3 2>&1 | grep "c5-like\|c3 atm"
+for nt in 256 128 256 128; do
+  echo "== MHB200_NT=$nt"
+  MHB200_NT=$nt timeout 300 python bench_micro/first_timing.py c1 c4 2>&1 | grep "c1 12x\|0.25deg\|single"
 done
