@@ -1,6 +1,7 @@
 #!/bin/bash
 set -x
-for nt in 256 128 256 128; do
-  echo "== MHB200_NT=$nt"
-  MHB200_NT=$nt timeout 300 python bench_micro/first_timing.py c1 c4 2>&1 | grep "c1 12x\|0.25deg\|single"
+MHB200_MOMENTS=1 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+for m in 0 1 0 1; do
+  echo "== MHB200_MOMENTS=$m"
+  MHB200_MOMENTS=$m timeout 300 python bench_micro/first_timing.py c3 2>&1 | grep cfg
 done

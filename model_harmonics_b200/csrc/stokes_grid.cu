@@ -42,6 +42,8 @@ constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
 constexpr int DF_MAX = 448;
 constexpr int MAX_PARTS = 16;
 constexpr int LEV_GROUP = 38;     // levels staged per geometry pass
+constexpr int NMOM = 16;          // binomial moments per column (see produce_atmosphere, MOM path)
+constexpr bool MOMENTS_DEFAULT = true;
 
 // CTA shape.  NTH threads handle chunks of up to NTH/2 longitudes.  NTH = 256 runs one CTA per
 // SM; NTH = 128 runs two, so that one CTA's produce phase overlaps the other's contraction
@@ -53,7 +55,11 @@ struct Shape {
   static constexpr int NW = NTH / 32;            // warps
   // region 0 holds the B chunk (KC x 64 doubles) and, before it is written, the staged (u0, r)
   // pairs of the atmosphere geometry pass (LEV_GROUP x KC x 16 B)
-  static constexpr int REGION0 = LEV_GROUP * KC * 2;
+  // ... and, in the binomial-moment produce path (NTH = 128), the B chunk followed by the chunk's
+  // NMOM x KC moment block
+  static constexpr int MOM_OFF = KS * 256;
+  static constexpr int REGION0 = (NTH == 128 && MOM_OFF + NMOM * KC > LEV_GROUP * KC * 2) ? MOM_OFF + NMOM * KC
+                                                                                         : LEV_GROUP * KC * 2;
   static_assert(REGION0 >= KS * 256, "region 0 must hold the B chunk");
   // + 16 doubles: the colatitude-only factors of the atmosphere geometry for this ring and the next
   static constexpr size_t SMEM = (size_t)(REGION0 + CS_ROWS * NTH + MBLK * PLM_PITCH + 16) * sizeof(double);
@@ -97,6 +103,10 @@ struct GridParams {
   long long geo_s0, geo_s1;
   const double *ring_tab, *lon_tab;
   int nlev;
+  // binomial-moment produce path: r^n = r0^n sum_j C(n,j) d^j, d = (r - r0)/r0
+  int mom;                     // 1: use it (fold level 2, one tile, 128-thread shape)
+  double mom_r0, mom_inv_r0;
+  const double* bmat;          // C(n,j) r0^n, n = l + 2 (BC05) or l + 4 (SW02), as DMMA B fragments [4][8][32]
 };
 
 struct ReduceParams {
@@ -537,14 +547,32 @@ struct NextCol {
   double geo, cphi, sphi;
 };
 
+// MOM path: one level's contribution to the 8 moments this thread owns: m[j] += w * d^(j + 8*UPPER)
+template <bool UPPER>
+__device__ __forceinline__ void accumulate_moments(double (&m)[8], double w, double d) {
+  const double d2 = d * d, d3 = d2 * d, d4 = d2 * d2;
+  const double d5 = d4 * d, d6 = d4 * d2, d7 = d4 * d3;
+  const double v = UPPER ? w * (d4 * d4) : w;
+  m[0] += v;
+  m[1] = fma(v, d, m[1]);
+  m[2] = fma(v, d2, m[2]);
+  m[3] = fma(v, d3, m[3]);
+  m[4] = fma(v, d4, m[4]);
+  m[5] = fma(v, d5, m[5]);
+  m[6] = fma(v, d6, m[6]);
+  m[7] = fma(v, d7, m[7]);
+}
+
 // per-column / per-ring constants of the atmosphere geometry
 struct ColumnGeom {
   double NG, NG1, cphi, sphi, geo_over;
   double a1, a2, st, ct, gs, c1, rad_e, inv_rad;
+  double r0, inv_r0;           // MOM path
 };
 
 // (u0, r) of GW (level, column) elements: u0 = -(dp/gamma) r^2 (BC05) or -(dp/g0) r^4 (SW02)
-template <int MODE>
+// MOM: (w, d) instead, w = -(dp/gamma) or -(dp/g0) and d = (r - r0)/r0 (the difference is exact).
+template <int MODE, bool MOM>
 __device__ __forceinline__ void level_elements(const double (&z)[GW], const double (&dpv)[GW],
                                                const ColumnGeom& c, double (&u0)[GW], double (&r)[GW]) {
   if (MODE == MODE_ATM_BC05) {
@@ -565,7 +593,12 @@ __device__ __forceinline__ void level_elements(const double (&z)[GW], const doub
 #pragma unroll
     for (int i = 0; i < GW; ++i) {
       r[i] = R[i] * c.inv_rad;
-      u0[i] = -(q[i] * r[i]) * r[i];
+      if (MOM) {
+        u0[i] = -q[i];
+        r[i] = (r[i] - c.r0) * c.inv_r0;
+      } else {
+        u0[i] = -(q[i] * r[i]) * r[i];
+      }
     }
   } else {
     double den[GW], num[GW], t[GW], q[GW], g0[GW];
@@ -580,8 +613,13 @@ __device__ __forceinline__ void level_elements(const double (&z)[GW], const doub
 #pragma unroll
     for (int i = 0; i < GW; ++i) {
       r[i] = t[i] + c.geo_over;
-      const double r2 = r[i] * r[i];
-      u0[i] = -(q[i] * r2) * r2;
+      if (MOM) {
+        u0[i] = -q[i];
+        r[i] = (r[i] - c.r0) * c.inv_r0;
+      } else {
+        const double r2 = r[i] * r[i];
+        u0[i] = -(q[i] * r2) * r2;
+      }
     }
   }
 }
@@ -597,7 +635,14 @@ __device__ __forceinline__ void level_elements(const double (&z)[GW], const doub
 //   accumulate pass : two threads (warps w, w + NW/2) share a column and split the 64 degrees;
 //                     32 running sums per thread in registers
 // ---------------------------------------------------------------------------------------
-template <int MODE, typename Tin, int NTH>
+// MOM (binomial-moment path, LMAX <= 63): with r = r0 (1 + d), r^n = r0^n sum_j C(n,j) d^j, so the
+// level sum only needs the NMOM moments  M_j = - sum_k (dp_k/gamma_k) d_k^j  per column (d <~ 0.01:
+// 16 moments reach rounding level for heights to ~100 km); the accumulate pass then costs 15 pipe
+// slots per (level, column) and thread instead of 43, the two threads of a column splitting the
+// moments.  The moments go to shared memory behind the B chunk; moments_to_chunk() folds them and
+// expands them to the 64 degrees with DMMA tiles.  Same 1e-12 contract (measured ~1e-15), different
+// rounding than the direct powers.
+template <int MODE, typename Tin, int NTH, bool MOM>
 __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, int h, int lb, int chunk,
                                                    double* Bs, const NextCol& nx, const double* ring_s) {
   constexpr int KC = Shape<NTH>::KC;
@@ -634,6 +679,8 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
     cg.rad_e = p.rad_e;
     cg.inv_rad = 1.0 / p.rad_e;
     cg.geo_over = geo / p.rad_e;
+    cg.r0 = p.mom_r0;
+    cg.inv_r0 = p.mom_inv_r0;
   }
   const size_t col0 = (size_t)t * p.batch_stride + (size_t)h * p.nlon + gpc;
   const Tin* zp = (const Tin*)p.GPH + col0;
@@ -644,9 +691,9 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
   constexpr int NWH = NTH / 64;
   const int half = warp / NWH;
   const int acol = (warp % NWH) * 32 + lane;
-  double acc[32];
+  double acc[MOM ? 8 : 32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+  for (int j = 0; j < (MOM ? 8 : 32); ++j) acc[j] = 0.0;
 
   for (int kg = 0; kg < nlev; kg += LEV_GROUP) {
     const int ng = min(LEV_GROUP, nlev - kg);
@@ -699,14 +746,14 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
             ds[i] = sp * (double)raw[8 / sizeof(Tin)];
           }
         }
-        level_elements<MODE>(zs, ds, cg, u0, r);
+        level_elements<MODE, MOM>(zs, ds, cg, u0, r);
 #pragma unroll
         for (int i = 0; i < GW; ++i) {
           const int e = b * GW + i;
-          if (lb > 0) u0[i] *= ipow(r[i], lb * LBLK);
+          if (!MOM && lb > 0) u0[i] *= ipow(r[i], lb * LBLK);
           if (!gactive) {
             u0[i] = 0.0;
-            r[i] = 1.0;
+            r[i] = MOM ? 0.0 : 1.0;
           }
           if (e < nmine) stg[(gpar + 2 * e) * KC + gcol] = make_double2(u0[i], r[i]);
         }
@@ -716,25 +763,94 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
     // warps (same 32 columns in both passes), so the hand-over is a 64-thread named barrier.
     asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp % NWH)) : "memory");
     // ---- accumulate pass
-    if (half) {
+    if constexpr (MOM) {
+      if (half) {
 #pragma unroll 4
-      for (int kk = 0; kk < ng; ++kk) {
-        const double2 e = stg[kk * KC + acol];
-        accumulate_level<true>(acc, e.x, e.y);
+        for (int kk = 0; kk < ng; ++kk) {
+          const double2 e = stg[kk * KC + acol];
+          accumulate_moments<true>(acc, e.x, e.y);
+        }
+      } else {
+#pragma unroll 4
+        for (int kk = 0; kk < ng; ++kk) {
+          const double2 e = stg[kk * KC + acol];
+          accumulate_moments<false>(acc, e.x, e.y);
+        }
       }
     } else {
+      if (half) {
 #pragma unroll 4
-      for (int kk = 0; kk < ng; ++kk) {
-        const double2 e = stg[kk * KC + acol];
-        accumulate_level<false>(acc, e.x, e.y);
+        for (int kk = 0; kk < ng; ++kk) {
+          const double2 e = stg[kk * KC + acol];
+          accumulate_level<true>(acc, e.x, e.y);
+        }
+      } else {
+#pragma unroll 4
+        for (int kk = 0; kk < ng; ++kk) {
+          const double2 e = stg[kk * KC + acol];
+          accumulate_level<false>(acc, e.x, e.y);
+        }
       }
     }
     __syncthreads();      // staging is overwritten by the next group / by the B chunk
   }
-  if (acol < p.kc) {
-    const int l0 = 32 * half;
+  if constexpr (MOM) {
+    // moment block [NMOM][KC] behind the B chunk (inactive columns hold zeros)
+    double* M = Bs + Shape<NTH>::MOM_OFF;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) Bs[b_slot(p, l0 + j, acol)] = acc[j];
+    for (int j = 0; j < 8; ++j) M[(8 * half + j) * KC + acol] = acc[j];
+  } else {
+    if (acol < p.kc) {
+      const int l0 = 32 * half;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Bs[b_slot(p, l0 + j, acol)] = acc[j];
+    }
+  }
+}
+
+// MOM path, after the produce phase: fold the chunk's moments over the four symmetric columns and
+// expand them to the 64 degrees,  B[c][l][j] = sum_i Mfold[c][i][j] * (C(n_l, i) r0^n_l),  as DMMA
+// tiles (rows = 8 contraction columns, k = moments, n = 8 degrees; the constant matrix comes from L1
+// as ready-made B fragments).  Warp w produces sub-buffer w (see fold_chunk for the four combinations).
+// Reads the moment block, writes the B chunk: disjoint, so no barrier in between.
+template <int NTH>
+__device__ __forceinline__ void moments_to_chunk(const GridParams& p, double* Bs) {
+  static_assert(NTH == 128, "one warp per sub-buffer");
+  constexpr int KC = Shape<NTH>::KC;
+  const double* M = Bs + Shape<NTH>::MOM_OFF;
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  const int row = lane >> 2, kk = lane & 3;
+  const double* bm = p.bmat + lane;
+  const int kcf = p.kcf, o = p.half_off;
+  for (int ct = 0; ct * 8 < kcf; ++ct) {
+    const int col = ct * 8 + row;
+    const bool ok = (col < kcf);
+    const int cc = ok ? col : 0;
+    double a[NMOM / 4];
+#pragma unroll
+    for (int ks = 0; ks < NMOM / 4; ++ks) {
+      const double* mj = M + (4 * ks + kk) * KC + cc;
+      const double x1 = mj[0], x2 = mj[kcf], x3 = mj[2 * kcf], x4 = mj[3 * kcf];
+      const double s12 = x1 + x2, d12 = x1 - x2, s34 = x3 + x4, d34 = x3 - x4;
+      const double v = (c == 0) ? s12 + s34 : (c == 1) ? d12 - d34 : (c == 2) ? s12 - s34 : d12 + d34;
+      a[ks] = ok ? v : 0.0;
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < NMOM / 4; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], a[ks], __ldg(bm + (ks * 8 + nt) * 32));
+    }
+    if (ok) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int l = nt * 8 + 2 * kk;
+        Bs[c * o + bs_index(l, col)] = acc[nt][0];
+        Bs[c * o + bs_index(l + 1, col)] = acc[nt][1];
+      }
+    }
   }
 }
 
@@ -857,10 +973,20 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
         else
           produce_pressure<NTH>(p, cell, seg.lb, Bs);
       } else {
-        produce_atmosphere<MODE, Tin, NTH>(p, seg.t, h, seg.lb, chunk, Bs, next_col, ring_s);
+        if constexpr (NTH == 128) {
+          if (p.mom) produce_atmosphere<MODE, Tin, NTH, true>(p, seg.t, h, seg.lb, chunk, Bs, next_col, ring_s);
+          else produce_atmosphere<MODE, Tin, NTH, false>(p, seg.t, h, seg.lb, chunk, Bs, next_col, ring_s);
+        } else {
+          produce_atmosphere<MODE, Tin, NTH, false>(p, seg.t, h, seg.lb, chunk, Bs, next_col, ring_s);
+        }
       }
       __syncthreads();
-      if (p.fold && !pfold) {
+      bool mom_path = false;
+      if constexpr (NTH == 128 && MODE != MODE_PRESSURE) mom_path = (p.mom != 0);
+      if (mom_path) {
+        if constexpr (NTH == 128) moments_to_chunk<NTH>(p, Bs);
+        __syncthreads();
+      } else if (p.fold && !pfold) {
         fold_chunk<NTH>(p, Bs);
         __syncthreads();
       }
@@ -1068,6 +1194,7 @@ struct mhb200_plan {
   double *f1 = nullptr, *f2 = nullptr, *pmm = nullptr, *sq = nullptr, *rescale = nullptr, *x = nullptr,
          *w = nullptr;
   double* ckpt = nullptr;  // Legendre restart states (nlb > 1)
+  double* bmat = nullptr;  // binomial-moment expansion matrices (nlb == 1): [BC05 | SW02][4][8][32] B fragments
   // longitude mirror folding: contraction column i pairs grid column colp[i] with its mirror
   // colq[i] (phi_q = -phi_p mod 2 pi; colq == colp for a self-mirrored column)
   int fold = 0;            // 0: none, 1: phi -> -phi, 2: also phi -> pi - phi
@@ -1219,6 +1346,25 @@ size_t max_segments(const mhb200_plan* pl, int nbatch) {
 // other's contraction) cover single-block problems (LMAX <= 63) in every mode -- measured on the
 // LMAX-60 pressure configs: 12 x 181x360 0.314 -> 0.264 ms, 721x1440 0.313 -> 0.295 ms;
 // MHB200_NT=128|256 forces a shape where legal.
+// Expansion point of the binomial-moment path: radius ratio about 17.6 km above the mean sphere, the
+// middle of what the ellipsoid (-21 km at the poles) and the level heights (to ~50 km) span, so that
+// |d| = |r/r0 - 1| stays below ~0.007 and 16 moments reach rounding level at degree 64.
+constexpr double MOM_R0 = 1.00276;
+
+// MHB200_MOMENTS=0|1 switches the binomial-moment produce path (atmosphere, fold level 2, LMAX <= 63)
+bool use_moments(const mhb200_plan* pl, const Variant& v, int mode) {
+  if (mode == MODE_PRESSURE || pl->fold != 2 || pl->nlb != 1 || v.nth != 128 || pl->bmat == nullptr) return false;
+  if (const char* e = getenv("MHB200_MOMENTS")) return atoi(e) != 0;
+  return MOMENTS_DEFAULT;
+}
+
+void set_moment_params(const mhb200_plan* pl, const Variant& v, int mode, GridParams& gp) {
+  gp.mom = use_moments(pl, v, mode) ? 1 : 0;
+  gp.mom_r0 = MOM_R0;
+  gp.mom_inv_r0 = 1.0 / MOM_R0;
+  gp.bmat = pl->bmat ? pl->bmat + (mode == MODE_ATM_SW02 ? (NMOM / 4) * 8 * 32 : 0) : nullptr;
+}
+
 int pick_variant(const mhb200_plan* pl, int mode) {
   (void)mode;
   int v = (pl->nlb == 1) ? 1 : 0;
@@ -1599,6 +1745,26 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
     return rc;
   }
   pl->ckpt = nullptr;
+  pl->bmat = nullptr;
+  if (pl->nlb == 1) {
+    // C(n, j) r0^n as DMMA B fragments: element [k = lane % 4][n-col = lane / 4] of tile (ks, nt) is
+    // moment j = 4 ks + lane % 4, degree l = 8 nt + lane / 4; n = l + 2 (BC05) or l + 4 (SW02)
+    std::vector<double> bm((size_t)2 * (NMOM / 4) * 8 * 32, 0.0);
+    for (int md = 0; md < 2; ++md)
+      for (int ks = 0; ks < NMOM / 4; ++ks)
+        for (int nt = 0; nt < 8; ++nt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int j = 4 * ks + (lane & 3), l = 8 * nt + (lane >> 2), n = l + (md ? 4 : 2);
+            if (l > pl->lmax || j > n) continue;
+            long double cnj = 1.0L;
+            for (int i = 1; i <= j; ++i) cnj = cnj * (long double)(n - j + i) / (long double)i;
+            bm[(((size_t)md * (NMOM / 4) + ks) * 8 + nt) * 32 + lane] = (double)(cnj * powl((long double)MOM_R0, n));
+          }
+    if ((rc = upload(&pl->bmat, bm)) != MHB200_OK) {
+      mhb200_plan_destroy(pl);
+      return rc;
+    }
+  }
   if (pl->nlb > 1) {
     // Legendre restart states at the degree-block boundaries, computed once on the device
     const size_t n = (size_t)nlat * pl->nlb * Mpad * 2;
@@ -1634,6 +1800,7 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   cudaFree(pl->w);
   cudaFree(pl->lb_first_tile_dev);
   if (pl->ckpt) cudaFree(pl->ckpt);
+  if (pl->bmat) cudaFree(pl->bmat);
   for (auto& sc : pl->band_sched) free_schedule(sc);
   for (auto& c : pl->cube_dev)
     if (c) cudaFree(c);
@@ -1741,6 +1908,7 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
   gp.lon_tab = lon_tab;
   gp.nlev = nlev;
   gp.rad_e = rad_e;
+  set_moment_params(pl, v, mode, gp);
   if (mode == MODE_ATM_BC05)
     rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_BC05, double>(gp, v, st)
                                : launch_ring<MODE_ATM_BC05, float>(gp, v, st);
@@ -1836,6 +2004,7 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
     gp.lon_tab = lon_tab;
     gp.nlev = nlev;
     gp.rad_e = rad_e;
+    set_moment_params(pl, v, mode, gp);
     Variant vb = v;           // launch with this band's CTA count
     vb.sched.ncta = sc.ncta;
     if (mode == MODE_ATM_BC05)

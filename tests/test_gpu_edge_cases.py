@@ -76,6 +76,29 @@ def test_points_boundary_sizes(n, L, M):
     assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
 
 
+@pytest.mark.parametrize('method', ['BC05', 'SW02'])
+def test_moment_path_and_direct_path_agree(monkeypatch, method):
+    """The binomial-moment produce path (default at fold level 2, LMAX <= 63) against the direct powers, both
+    against the oracle; 45 levels reaching 80 km also exercise two level groups and large |r/r0 - 1|."""
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    nlev, nlat, nlon, L = 45, 19, 48, 60
+    lat = np.linspace(90.0, -90.0, nlat)
+    lon = np.arange(nlon) * (360.0 / nlon)
+    GPH, dP, geoid = syn.atmosphere_cube(nlev, nlat, nlon, seed=77)
+    GPH = GPH * (80000.0 / GPH.max())            # top level at 80 km
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=geoid, LOVE=syn.love_numbers(L), METHOD=method)
+    ref = stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    out = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('MHB200_MOMENTS', flag)
+        out[flag] = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+        assert rel_to_max(out[flag].clm, out[flag].slm, ref.clm, ref.slm) <= TOL
+    monkeypatch.delenv('MHB200_MOMENTS')
+    assert rel_to_max(out['0'].clm, out['0'].slm, out['1'].clm, out['1'].slm) <= 1e-13
+    assert np.abs(out['0'].clm - out['1'].clm).max() > 0.0        # the two paths really are different code
+
+
 def test_pressure_lmax360_against_oracle():
     """High degree (21 tiles, FULL + DIAG paths, deep Legendre recursion incl. polar underflow)."""
     from oracle import stokes_oracle
