@@ -795,10 +795,12 @@ __device__ __forceinline__ void produce_atmosphere(const GridParams& p, int t, i
     __syncthreads();      // staging is overwritten by the next group / by the B chunk
   }
   if constexpr (MOM) {
-    // moment block [NMOM][KC] behind the B chunk (inactive columns hold zeros)
+    // moment block [NMOM][KC] behind the B chunk (inactive columns hold zeros); the column index is
+    // swizzled with the moment index so that moments_to_chunk's fragment loads (4 moments x 8 columns per
+    // warp) are bank-conflict free
     double* M = Bs + Shape<NTH>::MOM_OFF;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) M[(8 * half + j) * KC + acol] = acc[j];
+    for (int j = 0; j < 8; ++j) M[(8 * half + j) * KC + (acol ^ ((j & 3) << 2))] = acc[j];
   } else {
     if (acol < p.kc) {
       const int l0 = 32 * half;
@@ -829,8 +831,10 @@ __device__ __forceinline__ void moments_to_chunk(const GridParams& p, double* Bs
     double a[NMOM / 4];
 #pragma unroll
     for (int ks = 0; ks < NMOM / 4; ++ks) {
-      const double* mj = M + (4 * ks + kk) * KC + cc;
-      const double x1 = mj[0], x2 = mj[kcf], x3 = mj[2 * kcf], x4 = mj[3 * kcf];
+      const double* mj = M + (4 * ks + kk) * KC;
+      const int sw = kk << 2;                      // (moment index & 3) << 2, see produce_atmosphere
+      const double x1 = mj[cc ^ sw], x2 = mj[(kcf + cc) ^ sw], x3 = mj[(2 * kcf + cc) ^ sw],
+                   x4 = mj[(3 * kcf + cc) ^ sw];
       const double s12 = x1 + x2, d12 = x1 - x2, s34 = x3 + x4, d34 = x3 - x4;
       const double v = (c == 0) ? s12 + s34 : (c == 1) ? d12 - d34 : (c == 2) ? s12 - s34 : d12 + d34;
       a[ks] = ok ? v : 0.0;
