@@ -10,6 +10,8 @@ Host-side pieces the operators need from outside the hot path.
   check whether a caller-supplied ``PLM`` table is the standard one for ``lat``.
 """
 import copy as _copy
+import os as _os
+import re as _re
 
 import numpy as np
 
@@ -135,6 +137,58 @@ except Exception:
             out.clm = np.mean(self.clm, axis=-1)
             out.slm = np.mean(self.slm, axis=-1)
             return out
+
+        # --- text files (the on-disk format that needs neither netCDF4 nor h5py) --------
+        # One line per coefficient, order-major, "l m clm slm [time]" with the field widths of
+        # gravity_toolkit.harmonics.to_ascii v1.2.x (restated from the published format; the real class is
+        # used instead whenever gravity_toolkit is importable).  This is what the drivers call through
+        # Ylms.to_file(output_file, format='ascii') (reanalysis_atmospheric_harmonics.py:409-417).
+        def to_ascii(self, filename, date=True, **kwargs):
+            self.filename = _os.path.abspath(_os.path.expanduser(str(filename)))
+            fmt = '{0:5d} {1:5d} {2:+21.12e} {3:+21.12e}' + (' {4:10.4f}' if date else '')
+            with open(self.filename, mode='w', encoding='utf8') as fid:
+                for m in range(0, int(self.mmax) + 1):
+                    for l in range(m, int(self.lmax) + 1):
+                        args = (l, m, float(self.clm[l, m]), float(self.slm[l, m]))
+                        if date:
+                            args = args + (float(np.squeeze(self.time)),)
+                        print(fmt.format(*args), file=fid)
+            return self
+
+        def from_ascii(self, filename, date=True, **kwargs):
+            self.filename = _os.path.abspath(_os.path.expanduser(str(filename)))
+            number = _re.compile(r'[-+]?(?:(?:\d*\.\d+)|(?:\d+\.?))(?:[Ee][+-]?\d+)?')
+            rows = []
+            with open(self.filename, mode='r', encoding='utf8') as fid:
+                for line in fid.read().splitlines():
+                    vals = number.findall(line)
+                    if len(vals) >= 4:
+                        rows.append(vals)
+            if not rows:
+                raise ValueError('no coefficients in %s' % self.filename)
+            self.lmax = np.int64(max(int(v[0]) for v in rows))
+            self.mmax = np.int64(max(int(v[1]) for v in rows))
+            self.update_dimensions()
+            self.clm = np.zeros((self.lmax + 1, self.mmax + 1))
+            self.slm = np.zeros((self.lmax + 1, self.mmax + 1))
+            for v in rows:
+                l, m = int(v[0]), int(v[1])
+                self.clm[l, m] = np.float64(v[2])
+                self.slm[l, m] = np.float64(v[3])
+                if date and len(v) >= 5:
+                    self.time = np.float64(v[4])
+            return self
+
+        def to_file(self, filename, format=None, date=True, **kwargs):
+            if format not in ('ascii', None):
+                raise ValueError('the stand-in harmonics container writes ascii only '
+                                 '(netCDF4 / HDF5 need gravity_toolkit with netCDF4 / h5py)')
+            return self.to_ascii(filename, date=date, **kwargs)
+
+        def from_file(self, filename, format=None, date=True, **kwargs):
+            if format not in ('ascii', None):
+                raise ValueError('the stand-in harmonics container reads ascii only')
+            return self.from_ascii(filename, date=date, **kwargs)
 
 
 # name -> (semi-major axis [m], flattening), reference datum.py:121-189

@@ -136,3 +136,33 @@ def test_asymmetric_grid_does_not_fold():
     phi, sets, fold, nchunks, kcf = _fold(np.arange(90) * 4.0 + 0.7, 256)
     assert fold == 0 and np.all(sets[:, 1:] == -1) and np.array_equal(sets[:, 0], np.arange(90))
     assert kcf <= 128 and nchunks * kcf >= 90
+
+
+def test_harmonics_ascii_round_trip(tmp_path):
+    """SURVEY 8f-4, the part that needs neither netCDF4 nor h5py: the text format of
+    harmonics.to_ascii / from_ascii (one 'l m clm slm [time]' line per coefficient, order-major)."""
+    from model_harmonics_b200 import _compat
+    if _compat.HAVE_GRAVITY_TOOLKIT:
+        pytest.skip('the real gravity_toolkit container is in use')
+    rng = np.random.default_rng(5)
+    L, M = 12, 7
+    Y = _compat.harmonics(lmax=L, mmax=M)
+    Y.clm = np.tril(rng.standard_normal((L + 1, L + 1)))[:, :M + 1] * 1e-9
+    Y.slm = np.tril(rng.standard_normal((L + 1, L + 1)), -1)[:, :M + 1] * 1e-9
+    Y.time = 2003.4567
+    path = tmp_path / 'ERA5_CLM_L12M7_016.txt'
+    Y.to_file(path, format='ascii')
+    lines = path.read_text().splitlines()
+    assert len(lines) == sum(L + 1 - m for m in range(M + 1))
+    assert lines[0] == '{0:5d} {1:5d} {2:+21.12e} {3:+21.12e} {4:10.4f}'.format(0, 0, Y.clm[0, 0], 0.0, 2003.4567)
+    Z = _compat.harmonics().from_file(path, format='ascii')
+    assert (int(Z.lmax), int(Z.mmax)) == (L, M) and Z.time == 2003.4567
+    # 13 significant digits survive the text form
+    assert np.allclose(Z.clm, Y.clm, rtol=1e-12, atol=0.0) and np.allclose(Z.slm, Y.slm, rtol=1e-12, atol=0.0)
+    with pytest.raises(ValueError):
+        Y.to_file(path, format='netCDF4')
+    # without a date column
+    Y.to_ascii(path, date=False)
+    assert len(path.read_text().splitlines()[0].split()) == 4
+    W = _compat.harmonics().from_ascii(path, date=False)
+    assert np.allclose(W.clm, Y.clm, rtol=1e-12, atol=0.0)
