@@ -249,3 +249,42 @@ def plm_columns(lmax, mmax, x, samples):
             p1, p2 = x * f1 * p1 - f2 * p2, p1
         out[i] = p1 * rescale
     return out
+
+
+def plm_table(lmax, mmax, x):
+    """
+    The full standard table P_lm(x), shape (lmax+1, mmax+1, len(x)): the same recursion as
+    ``plm_columns`` for every (l, m <= l).  Used once per plan to decide whether a caller-supplied
+    ``PLM`` is the standard table (then it is regenerated on the fly) or must be used as given.
+    """
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    u = np.sqrt(1.0 - x**2)
+    u[u == 0] = np.finfo(np.float64).eps
+    out = np.zeros((lmax + 1, mmax + 1, len(x)))
+    scalef = 1.0e-280
+    pmm = np.sqrt(2.0) * scalef
+    rescale = np.full_like(x, 1.0 / scalef)
+    for m in range(0, mmax + 1):
+        if m == 0:
+            pm, rs = 1.0, np.ones_like(x)
+        else:
+            pmm = pmm * np.sqrt(2 * m + 1) / np.sqrt(2 * m)
+            rescale = rescale * u
+            pm, rs = pmm, rescale
+        p2 = np.full_like(x, pm)
+        out[m, m] = p2 * rs
+        if m + 1 > lmax:
+            continue
+        p1 = x * np.sqrt(2 * m + 3) * pm
+        out[m + 1, m] = p1 * rs
+        for ll in range(m + 2, lmax + 1):
+            if m == 0:
+                f1 = np.sqrt(2.0 * ll - 1.0) * np.sqrt(2.0 * ll + 1.0) / ll
+                f2 = (ll - 1.0) * np.sqrt(2.0 * ll + 1.0) / (np.sqrt(2.0 * ll - 3.0) * ll)
+            else:
+                f1 = np.sqrt(2.0 * ll + 1.0) * np.sqrt(2.0 * ll - 1.0) / (np.sqrt(ll + m) * np.sqrt(ll - m))
+                f2 = np.sqrt(2.0 * ll + 1.0) * np.sqrt(ll - m - 1.0) * np.sqrt(ll + m - 1.0) / \
+                    (np.sqrt(2.0 * ll - 3.0) * np.sqrt(ll + m) * np.sqrt(ll - m))
+            p1, p2 = x * f1 * p1 - f2 * p2, p1
+            out[ll, m] = p1 * rs
+    return out

@@ -25,6 +25,7 @@
 // rather than specialising warps.
 #include "../../include/mhb200.h"
 #include "common.cuh"
+#include "grid_plan.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -34,16 +35,13 @@
 
 namespace mhb {
 
-constexpr int LBLK = 64;          // degrees per block
-constexpr int MBLK = 64;          // orders per block
 constexpr int PLM_PITCH = 65;
 constexpr int CS_ROWS = 40;       // per-thread accumulators kept in shared memory (10 sub-tiles x cos,sin x 2)
 constexpr int SLOT_DOUBLES = 2 * LBLK * MBLK;
 constexpr int DF_MAX = 448;
-constexpr int MAX_PARTS = 16;
 constexpr int LEV_GROUP = 38;     // levels staged per geometry pass
 constexpr int NMOM = 16;          // binomial moments per column (see produce_atmosphere, MOM path)
-constexpr bool MOMENTS_DEFAULT = true;
+constexpr bool MOMENTS_DEFAULT = false;   // opt-in (MHB200_MOMENTS=1): unguarded, superseded by stokes_moments.cu
 
 // CTA shape.  NTH threads handle chunks of up to NTH/2 longitudes.  NTH = 256 runs one CTA per
 // SM; NTH = 128 runs two, so that one CTA's produce phase overlaps the other's contraction
@@ -67,10 +65,6 @@ struct Shape {
 
 enum Mode { MODE_PRESSURE = 0, MODE_ATM_BC05 = 1, MODE_ATM_SW02 = 2 };
 
-// work unit = (ring, longitude chunk), linearised as u = ring * nchunks + chunk
-struct Segment {
-  int t, lb, mb, u0, u1, pad;
-};
 
 struct GridParams {
   int nlat, nlon, lmax, mmax, Mpad, kc, nchunks, nks_total;
@@ -107,6 +101,9 @@ struct GridParams {
   int mom;                     // 1: use it (fold level 2, one tile, 128-thread shape)
   double mom_r0, mom_inv_r0;
   const double* bmat;          // C(n,j) r0^n, n = l + 2 (BC05) or l + 4 (SW02), as DMMA B fragments [4][8][32]
+  // guarded fallback of the contracted-moment path (stokes_moments.cu): when non-null the kernel runs only if
+  // the flag is set (some |d| left the validated range), otherwise it exits at once
+  const int* run_flag;
 };
 
 struct ReduceParams {
@@ -121,6 +118,7 @@ struct ReduceParams {
   int nparts;
   const int* part_tsb[MAX_PARTS];
   int slot_off[MAX_PARTS];
+  const int* run_flag;          // see GridParams::run_flag
   double dfactor[DF_MAX];       // degree factors travel as kernel parameters
 };
 
@@ -1110,6 +1108,7 @@ __device__ __forceinline__ void run_segment(const GridParams& p, const Segment s
 
 template <int MODE, typename Tin, int NTH>
 __global__ void __launch_bounds__(NTH, 256 / NTH) stokes_ring_kernel(const GridParams p) {
+  if (p.run_flag != nullptr && *reinterpret_cast<const volatile int*>(p.run_flag) == 0) return;
   extern __shared__ double smem[];
   double* Bs = smem;
   double* Cs = Bs + Shape<NTH>::REGION0;
@@ -1129,6 +1128,7 @@ __global__ void __launch_bounds__(NTH, 256 / NTH) stokes_ring_kernel(const GridP
 // grid (lmax+1, nbatch), 256 threads: 4 interleaved partial sums per (l, m) -- independent
 // loads in flight -- combined in a fixed order, so results are bit-reproducible.
 __global__ void __launch_bounds__(256) stokes_reduce_kernel(const __grid_constant__ ReduceParams q) {
+  if (q.run_flag != nullptr && *reinterpret_cast<const volatile int*>(q.run_flag) == 0) return;
   __shared__ double part[2][4][MBLK];
   const int l = blockIdx.x, t = blockIdx.y;
   const int ncol = q.mmax + 1;
@@ -1172,54 +1172,6 @@ __global__ void __launch_bounds__(256) stokes_reduce_kernel(const __grid_constan
 // host side: plan, schedule, entry points
 // =========================================================================================
 using namespace mhb;
-
-struct Schedule {
-  int nbatch = -1, nlev = -1, mode = -1, h0 = -1, h1 = -1;
-  int ncta = 0, nseg = 0;
-  Segment* segs_dev = nullptr;
-  int* cta_seg_begin_dev = nullptr;
-  int* tile_slot_begin_dev = nullptr;
-};
-
-// longitude chunking + trig table for one CTA shape (variant 0: 256 threads, 1: 128 threads)
-struct Variant {
-  int nth = 0, ctas_per_sm = 1;
-  int kc = 0, kcf = 0, nchunks = 0, nks_total = 0;   // thread columns / contraction columns per chunk
-  double* trig = nullptr;
-  int* phys = nullptr;                               // [nchunks][kc] grid column of each thread column
-  int *pf_cols = nullptr, *pf_count = nullptr;       // L2 prefetch line lists (GridParams::pf_cols)
-  Schedule sched;
-};
-
-struct mhb200_plan {
-  int device, nlat, nlon, lmax, mmax;
-  int nlb, nmb, Mpad, ntiles, num_sms;
-  Variant var[2];
-  double *f1 = nullptr, *f2 = nullptr, *pmm = nullptr, *sq = nullptr, *rescale = nullptr, *x = nullptr,
-         *w = nullptr;
-  double* ckpt = nullptr;  // Legendre restart states (nlb > 1)
-  double* bmat = nullptr;  // binomial-moment expansion matrices (nlb == 1): [BC05 | SW02][4][8][32] B fragments
-  // longitude mirror folding: contraction column i pairs grid column colp[i] with its mirror
-  // colq[i] (phi_q = -phi_p mod 2 pi; colq == colp for a self-mirrored column)
-  int fold = 0;            // 0: none, 1: phi -> -phi, 2: also phi -> pi - phi
-  std::vector<int> colp, colq, colp2, colq2;
-  // host-pipelined atmosphere path: per-band schedules, device cubes, copy stream
-  Schedule band_sched[MAX_PARTS];
-  void* cube_dev[2] = {nullptr, nullptr};
-  size_t cube_bytes = 0;
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t band_ev[MAX_PARTS] = {};
-  cudaEvent_t done_ev = nullptr;
-  double* out_dev = nullptr;      // 2 x (lmax+1)(mmax+1)
-  double* out_pinned = nullptr;
-  int* lb_first_tile_dev = nullptr;
-  std::vector<int> lb_first_tile;
-  // per-call staging (field scales, long degree-factor vectors), grown on demand
-  double* stage_dev = nullptr;
-  size_t stage_doubles = 0;
-  size_t stage_reserved = 0;   // doubles at the front of the staging buffer used by field scales
-  std::mutex mu;
-};
 
 namespace {
 
@@ -1358,7 +1310,7 @@ constexpr double MOM_R0 = 1.00276;
 // MHB200_MOMENTS=0|1 switches the binomial-moment produce path (atmosphere, fold level 2, LMAX <= 63)
 bool use_moments(const mhb200_plan* pl, const Variant& v, int mode) {
   if (mode == MODE_PRESSURE || pl->fold != 2 || pl->nlb != 1 || v.nth != 128 || pl->bmat == nullptr) return false;
-  if (const char* e = getenv("MHB200_MOMENTS")) return atoi(e) != 0;
+  if (const char* e = getenv("MHB200_MOMENTS")) return atoi(e) == 1;
   return MOMENTS_DEFAULT;
 }
 
@@ -1420,8 +1372,9 @@ int launch_ring(const GridParams& gp, const Variant& v, cudaStream_t st) {
 }
 
 int finish_reduce(mhb200_plan* pl, const Variant& v, const double* dfactor, int nbatch, double* slots,
-                  double* clm, double* slm, cudaStream_t st) {
+                  double* clm, double* slm, cudaStream_t st, const int* run_flag = nullptr) {
   ReduceParams q;
+  q.run_flag = run_flag;
   q.dfactor_dev = nullptr;
   if (pl->lmax + 1 <= DF_MAX) {
     for (int l = 0; l <= pl->lmax; ++l) q.dfactor[l] = dfactor[l];
@@ -1750,6 +1703,10 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   }
   pl->ckpt = nullptr;
   pl->bmat = nullptr;
+  if ((rc = moment_plan_create(pl, phi)) != MHB200_OK) {
+    mhb200_plan_destroy(pl);
+    return rc;
+  }
   if (pl->nlb == 1) {
     // C(n, j) r0^n as DMMA B fragments: element [k = lane % 4][n-col = lane / 4] of tile (ks, nt) is
     // moment j = 4 ks + lane % 4, degree l = 8 nt + lane / 4; n = l + 2 (BC05) or l + 4 (SW02)
@@ -1805,6 +1762,7 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   cudaFree(pl->lb_first_tile_dev);
   if (pl->ckpt) cudaFree(pl->ckpt);
   if (pl->bmat) cudaFree(pl->bmat);
+  moment_plan_destroy(pl);
   for (auto& sc : pl->band_sched) free_schedule(sc);
   for (auto& c : pl->cube_dev)
     if (c) cudaFree(c);
@@ -1819,17 +1777,26 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   return MHB200_OK;
 }
 
+// A workspace is the partial-sum slots of the direct kernels followed by the region of the contracted-moment
+// path (stokes_moments.cu), which starts at a 256-byte boundary.
+static size_t slots_bytes(const mhb200_plan* pl, int nbatch) {
+  return (max_segments(pl, nbatch) * SLOT_DOUBLES * sizeof(double) + 255) & ~(size_t)255;
+}
+static size_t host_slots_bytes(const mhb200_plan* pl, int nbands) {
+  // every band is its own launch with its own segments
+  return ((size_t)nbands * max_segments(pl, 1) * SLOT_DOUBLES * sizeof(double) + 255) & ~(size_t)255;
+}
+
 size_t mhb200_grid_workspace_bytes(const mhb200_plan* pl, int nbatch, int nlev) {
   (void)nlev;
   if (!pl || nbatch < 1) return 0;
-  return max_segments(pl, nbatch) * SLOT_DOUBLES * sizeof(double);
+  return slots_bytes(pl, nbatch) + moment_workspace_bytes(pl, nbatch, 1);
 }
 
 size_t mhb200_host_workspace_bytes(const mhb200_plan* pl, int nbands) {
   if (!pl || nbands < 1) return 0;
   nbands = std::min(nbands, MAX_PARTS);
-  // every band is its own launch with its own segments
-  return (size_t)nbands * max_segments(pl, 1) * SLOT_DOUBLES * sizeof(double);
+  return host_slots_bytes(pl, nbands) + moment_workspace_bytes(pl, 1, nbands);
 }
 
 int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const int64_t Ps[3], const double* G,
@@ -1913,6 +1880,17 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
   gp.nlev = nlev;
   gp.rad_e = rad_e;
   set_moment_params(pl, v, mode, gp);
+  // Contracted-moment path (stokes_moments.cu) where the grid and the cubes allow it; the direct kernels
+  // below then only run (on the exact direct powers) if it flagged a radius outside its validated range.
+  if (moment_atm_eligible(pl, dtype, GPH, dP, batch_stride, nbatch, plm_table)) {
+    const int* flag = nullptr;
+    rc = moment_atm_run(pl, method, dtype, GPH, dP, batch_stride, gp.field_scale, geoid, gp.geo_s0, gp.geo_s1,
+                        ring_tab, nlev, nbatch, rad_e, dfactor, clm_out, slm_out,
+                        (char*)workspace + slots_bytes(pl, nbatch), &flag, st);
+    if (rc != MHB200_OK) return rc;
+    gp.run_flag = flag;
+    gp.mom = 0;
+  }
   if (mode == MODE_ATM_BC05)
     rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_BC05, double>(gp, v, st)
                                : launch_ring<MODE_ATM_BC05, float>(gp, v, st);
@@ -1920,7 +1898,7 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
     rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_SW02, double>(gp, v, st)
                                : launch_ring<MODE_ATM_SW02, float>(gp, v, st);
   if (rc != MHB200_OK) return rc;
-  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st, gp.run_flag);
 }
 
 
@@ -1979,7 +1957,14 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
   GridParams gp;
   ReduceParams q;
   q.nparts = nbands;
+  q.run_flag = nullptr;
   int slot_off = 0;
+  // contracted-moment path per band (the device cubes are cudaMalloc'ed: aligned for TMA)
+  const bool mom = moment_atm_eligible(pl, dtype, pl->cube_dev[0], pl->cube_dev[1], 0, 1, plm_table);
+  void* mom_ws = (char*)workspace + host_slots_bytes(pl, nbands);
+  const int* mom_flag = nullptr;
+  int mom_slots = 0;
+  if (mom && (rc = moment_band_begin(pl, nbands, mom_ws, &mom_flag, st)) != MHB200_OK) return rc;
   for (int b = 0; b < nbands; ++b) {
     const int h0 = (int)((long long)pl->nlat * b / nbands), h1 = (int)((long long)pl->nlat * (b + 1) / nbands);
     // band copy: nlev rows of (h1-h0)*nlon elements, pitch = one (lat, lon) plane
@@ -2009,6 +1994,13 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
     gp.nlev = nlev;
     gp.rad_e = rad_e;
     set_moment_params(pl, v, mode, gp);
+    if (mom) {
+      if ((rc = moment_band_launch(pl, nbands, method, dtype, pl->cube_dev[0], pl->cube_dev[1], geoid, gp.geo_s0,
+                                   gp.geo_s1, ring_tab, nlev, rad_e, h0, h1, &mom_slots, mom_ws, st)) != MHB200_OK)
+        return rc;
+      gp.run_flag = mom_flag;
+      gp.mom = 0;
+    }
     Variant vb = v;           // launch with this band's CTA count
     vb.sched.ncta = sc.ncta;
     if (mode == MODE_ATM_BC05)
@@ -2040,6 +2032,12 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
   q.slots = (const double*)workspace;
   q.clm = pl->out_dev;
   q.slm = pl->out_dev + nout;
+  if (mom) {
+    if ((rc = moment_band_finish(pl, nbands, method, mom_slots, dfactor, pl->out_dev, pl->out_dev + nout, mom_ws,
+                                 st)) != MHB200_OK)
+      return rc;
+    q.run_flag = mom_flag;
+  }
   stokes_reduce_kernel<<<dim3(pl->lmax + 1, 1), 256, 0, st>>>(q);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());

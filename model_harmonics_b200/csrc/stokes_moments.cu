@@ -1,0 +1,1137 @@
+// Contracted-moment form of the gridded fields -> Stokes path on B200 (sm_100a).
+//
+// Replaces the same reference loops as stokes_grid.cu (paths relative to the reference tree):
+//   model_harmonics/gen_atmosphere_stokes.py:217-275    geometry pre-pass, level loop, einsum
+//   model_harmonics/gen_pressure_stokes.py:194-206      per-degree power pass + complex einsum
+//
+// Per latitude ring h the radius ratio is written r = r0(h) (1 + d) with a ring-wide expansion
+// point r0(h), so that  r^n = r0^n sum_j C(n, j) d^j  and the per-degree radial factor needs only
+// NMOM = 16 moments per column,
+//   atmosphere:  M_j[p] = sum_k (dp_k / gamma_k) d_k^j        pressure:  M_j[p] = (P/G) d^j .
+// The binomial expansion, the Fourier sum over longitude and the Legendre sum over latitude are all
+// linear, so they commute; the expansion is applied LAST, once per coefficient:
+//   K_A  (atm_moment_kernel / pressure_moment_kernel)
+//        F[slot][m][cs][j] = sum_p {cos, sin}(m phi_p) M_j[p]         DMMA m8n8k4, N = 16 moments
+//        (a slot is one ring, or the part of a ring a CTA owned); atmosphere cubes arrive through a
+//        TMA pipeline (cp.async.bulk.tensor 4-D boxes: 64 longitudes x 4 levels per fold sub-block)
+//   K_B  (legendre_moment_kernel)   per order m, DMMA over slots:
+//        G[l][m][cs][j] = sum_slots w_h Plm(x_h) r0(h)^(l+n0) F[slot][m][cs][j]
+//        with Plm from the Holmes-Featherstone recursion generated on the fly (never materialised)
+//   K_C  (moment_finalize_kernel)
+//        C_lm, S_lm = dfactor[l] sum_j C(l + n0, j) G[l][m][{cos, sin}][j]
+// Same terms as the reference's sum, different summation order (1e-12 contract, measured ~1e-15).
+//
+// Validity: the truncated tail is (n |d|)^16 / 16!, so K_A tracks max |d| against 0.8 / n_max and
+// raises a flag; the caller then re-runs the call on the direct-power kernels of stokes_grid.cu
+// (launched unconditionally, they exit at once while the flag is clear), which are exact for any radius
+// like the reference's np.power.
+#include "../../include/mhb200.h"
+#include "common.cuh"
+#include "grid_plan.cuh"
+
+#include <cuda.h>     // CUtensorMap types; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace mhb {
+
+constexpr int NMOMC = 16;                 // moments per column
+constexpr int MKCF = 64;                  // contraction columns per chunk
+constexpr int MKC = 4 * MKCF;             // thread columns per chunk (four fold sub-blocks)
+constexpr int MLG = 4;                    // levels per TMA stage
+constexpr int MSTAGES = 4;                // stages in flight per CTA
+constexpr int MF_KS = 68;                 // folded-moment buffer: doubles per k-step (2 n-tiles x 32, +4 pad)
+constexpr int MF_V = 16 * MF_KS + 8;      // ... per fold variant (+8: variants land on different banks)
+constexpr int NB_SUB = 8;                 // fields per K_A launch (bounds the F workspace)
+constexpr int MAX_SPLIT = 8;              // ring splits of K_B
+constexpr int G_UNIT = 4 * 8 * 64;        // doubles K_B writes per (field, split, unit): 4 row tiles x 8 n-tiles
+constexpr double MOM_CENTER_HEIGHT = 24000.0;   // expansion point above the ellipsoid [m] (atmosphere)
+constexpr double MOM_ND_BOUND = 0.8;      // guard: n_max |d| <= 0.8  ->  (0.8)^16 / 16! = 1.3e-15
+
+// ------------------------------------------------------------------------------------------------
+// device helpers: mbarrier + TMA (raw PTX), Newton division / square root W elements wide
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// q = n / d and sqrt(a), W independent elements wide (statement by statement across the elements so that
+// the instruction stream carries the ILP): fp64 SFU seed, one Newton step, one residual correction --
+// correctly rounded in the geometry pass's ranges (bench_micro/newton_check.cu, profiles/r01_newton_check.jsonl)
+template <int W>
+__device__ __forceinline__ void div_t(const double (&n)[W], const double (&d)[W], double (&q)[W]) {
+  double y[W], e[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(d[i]));
+#pragma unroll
+  for (int i = 0; i < W; ++i) e[i] = fma(-d[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < W; ++i) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < W; ++i) q[i] = n[i] * y[i];
+#pragma unroll
+  for (int i = 0; i < W; ++i) e[i] = fma(-d[i], q[i], n[i]);
+#pragma unroll
+  for (int i = 0; i < W; ++i) q[i] = fma(e[i], y[i], q[i]);
+}
+template <int W>
+__device__ __forceinline__ void sqrt_t(const double (&a)[W], double (&g)[W]) {
+  double h[W], r[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a[i]));
+    g[i] = a[i] * y;
+    h[i] = 0.5 * y;
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) r[i] = fma(-g[i], h[i], 0.5);
+#pragma unroll
+  for (int i = 0; i < W; ++i) g[i] = fma(g[i], r[i], g[i]);
+#pragma unroll
+  for (int i = 0; i < W; ++i) h[i] = fma(h[i], r[i], h[i]);
+#pragma unroll
+  for (int i = 0; i < W; ++i) r[i] = fma(-g[i], g[i], a[i]);
+#pragma unroll
+  for (int i = 0; i < W; ++i) g[i] = fma(r[i], h[i], g[i]);
+}
+
+// m[j] += w d^j, j < 16:  7 products + 16 accumulates
+__device__ __forceinline__ void accumulate16(double (&m)[NMOMC], double w, double d) {
+  const double d2 = d * d, d3 = d2 * d, d4 = d2 * d2;
+  const double v4 = w * d4, d8 = d4 * d4;
+  const double v8 = w * d8, v12 = v8 * d4;
+  m[0] += w;
+  m[1] = fma(w, d, m[1]);
+  m[2] = fma(w, d2, m[2]);
+  m[3] = fma(w, d3, m[3]);
+  m[4] += v4;
+  m[5] = fma(v4, d, m[5]);
+  m[6] = fma(v4, d2, m[6]);
+  m[7] = fma(v4, d3, m[7]);
+  m[8] += v8;
+  m[9] = fma(v8, d, m[9]);
+  m[10] = fma(v8, d2, m[10]);
+  m[11] = fma(v8, d3, m[11]);
+  m[12] += v12;
+  m[13] = fma(v12, d, m[13]);
+  m[14] = fma(v12, d2, m[14]);
+  m[15] = fma(v12, d3, m[15]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_A, atmosphere
+// ------------------------------------------------------------------------------------------------
+struct AtmMomParams {
+  int nlat, nlon, nlev, nchunks, ngroups;
+  int h0, nrings;              // rings [h0, h0 + nrings) of every field of the launch
+  int t0;                      // first field of the launch (index into field_scale)
+  int fields_in_map;           // 1: all fields share the base cube (coordinate 0)
+  const int* cta_unit;         // [ncta + 1] unit span of every CTA; unit = (field, ring, chunk) linearised
+  const int* cta_slot;         // [ncta] first slot of the CTA's span
+  int slot_base;               // slots of this launch start here
+  const int* box_start;        // [nchunks][4] first longitude of the TMA box of every fold sub-block
+  const int* col_grid;         // [nchunks][256] grid column of thread column (warp, lane), -1 = inactive
+  int dir[4];                  // +1: sub-block runs ascend with the contraction column, -1: descend
+  const double* ring_tab;      // caller's 9 x nlat table (see mhb200.h)
+  const double* geoid;
+  long long geo_s0, geo_s1;
+  const double* field_scale;   // device, 2 per field, or null
+  const double* trig;          // A fragments [nchunks * 16][16 row tiles][32 lanes], order block 0
+  double* F;                   // [slot][64 orders][cs][16 moments]
+  double* slot_r0;
+  int* slot_ring;
+  int* flag;
+  double rad_e, inv_rad, hc;
+  unsigned dbound_hi;          // high word of the |d| bound
+};
+
+struct ColumnC {
+  // BC05: a1, a2 orthometric-height factors (field scale folded in), st, ct, g0..g2 normal gravity
+  // gam = g0 + H (g1 + g2 H), NG = N + geoid, NG1 = N (1 - e^2) + geoid, cinv = 1 / (rad_e r0)
+  // SW02: rad_e, sg, inv_r0, c0 = geoid / (rad_e r0) - 1
+  double a1, a2, st, ct, g0, g1, g2, NG, NG1, cinv;
+  double rad_e, sg, inv_r0, c0;
+};
+
+// (w, d) of W (level, column) elements:  w = dp / gamma (BC05) or dp (SW02; 1/g0 is applied at the flush),
+// d = r / r0 - 1.  Reference lines: gen_atmosphere_stokes.py:222-238 (BC05), :258-260 (SW02).
+// X^2 + Y^2 is formed as ((N + geoid + H) sin(theta))^2: cos^2(phi) + sin^2(phi) differs from 1 by rounding only.
+template <int MODE, int W>
+__device__ __forceinline__ void moment_elements(const double (&z)[W], const double (&dpv)[W], const ColumnC& c,
+                                                double (&w)[W], double (&d)[W]) {
+  if (MODE == MHB200_METHOD_BC05) {
+    double H[W], S[W], R[W], gam[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) H[i] = z[i] * fma(c.a2, z[i], c.a1);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const double As = (c.NG + H[i]) * c.st, Zz = (c.NG1 + H[i]) * c.ct;
+      S[i] = fma(Zz, Zz, As * As);
+      gam[i] = fma(H[i], fma(c.g2, H[i], c.g1), c.g0);
+    }
+    sqrt_t<W>(S, R);
+    div_t<W>(dpv, gam, w);
+#pragma unroll
+    for (int i = 0; i < W; ++i) d[i] = fma(R[i], c.cinv, -1.0);
+  } else {
+    double den[W], num[W], t[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      den[i] = fma(-c.sg, z[i], c.rad_e);
+      num[i] = c.rad_e;
+    }
+    div_t<W>(num, den, t);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      d[i] = fma(t[i], c.inv_r0, c.c0);
+      w[i] = dpv[i];
+    }
+  }
+}
+
+template <int MODE, int W>
+__device__ __forceinline__ void moment_levels(const double (&z)[W], const double (&dpv)[W], const ColumnC& c,
+                                              double (&acc)[NMOMC], unsigned bound_hi, int& viol) {
+  double w[W], d[W];
+  moment_elements<MODE, W>(z, dpv, c, w, d);
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    viol |= ((unsigned)(__double2hiint(d[i]) & 0x7fffffff) > bound_hi) ? 1 : 0;
+    accumulate16(acc, w[i], d[i]);
+  }
+}
+
+template <int MODE, typename Tin>
+__global__ void __launch_bounds__(256, 2)
+atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmP,
+                  const __grid_constant__ AtmMomParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  constexpr int STAGE_ELEMS = 2 * 4 * MLG * MKCF;
+  constexpr uint32_t STAGE_BYTES = STAGE_ELEMS * sizeof(Tin);
+  Tin* stages = reinterpret_cast<Tin*>(smraw);
+  double* Mf = reinterpret_cast<double*>(smraw + MSTAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(Mf + 4 * MF_V);
+  uint64_t* empty = full + MSTAGES;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane >> 3, jj = warp * 8 + (lane & 7);
+  const int u_begin = p.cta_unit[blockIdx.x], u_end = p.cta_unit[blockIdx.x + 1];
+  if (u_begin >= u_end) return;
+  if (tid == 0) {
+    for (int s = 0; s < MSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int ngroups = p.ngroups, nchunks = p.nchunks;
+  const int units_per_field = p.nrings * nchunks;
+  const int nitems = (u_end - u_begin) * ngroups;
+  // Producer side of the pipeline: item n = (unit, level group) goes to stage n % MSTAGES.  The warp
+  // n % 8 issues it (one lane), so the issue cost is spread over the CTA; before refilling a stage it
+  // waits until all 8 warps have read the item that was there.
+  auto issue = [&](int n) {
+    if (n >= nitems || warp != (n & 7) || lane != 0) return;
+    const int s = n % MSTAGES, k = n / MSTAGES;
+    if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+    const int u = u_begin + n / ngroups, g = n % ngroups;
+    const int t = u / units_per_field, rem = u - t * units_per_field;
+    const int h = p.h0 + rem / nchunks, c = rem % nchunks;
+    const int tf = (p.fields_in_map > 1) ? t : 0;
+    mbar_expect_tx(&full[s], STAGE_BYTES);
+    Tin* dst = stages + (size_t)s * STAGE_ELEMS;
+    const int* bs = p.box_start + c * 4;
+#pragma unroll
+    for (int sb = 0; sb < 4; ++sb) {
+      const int x0 = __ldg(bs + sb);
+      tma_load_4d(dst + sb * MLG * MKCF, &tmZ, &full[s], x0, h, g * MLG, tf);
+      tma_load_4d(dst + (4 + sb) * MLG * MKCF, &tmP, &full[s], x0, h, g * MLG, tf);
+    }
+  };
+  for (int n = 0; n < MSTAGES - 1; ++n) issue(n);
+
+  const int pos = (p.dir[sub] > 0) ? jj : (MKCF - 1 - jj);
+  const int par = warp >> 2, gi = warp & 3;          // contraction role: order parity and group of 16 orders
+  double facc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) (&facc[0][0][0])[i] = 0.0;
+  int viol = 0;
+  int slot = p.slot_base + p.cta_slot[blockIdx.x];
+  int item = 0;
+
+  // geoid of this thread's column, fetched one unit ahead
+  auto column_of = [&](int u, int& col, double& geo) {
+    const int t = u / units_per_field, rem = u - t * units_per_field;
+    const int h = p.h0 + rem / nchunks, c = rem % nchunks;
+    col = __ldg(p.col_grid + c * MKC + tid);
+    geo = (col >= 0 && p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + col * p.geo_s1) : 0.0;
+  };
+  int col_next;
+  double geo_next;
+  column_of(u_begin, col_next, geo_next);
+
+  for (int u = u_begin; u < u_end; ++u) {
+    const int t = u / units_per_field, rem = u - t * units_per_field;
+    const int h = p.h0 + rem / nchunks, c = rem % nchunks;
+    const bool active = (col_next >= 0);
+    const double geo = geo_next;
+    double sg = 1.0, sp = 1.0;
+    if (p.field_scale != nullptr) {
+      sg = __ldg(p.field_scale + 2 * (p.t0 + t));
+      sp = __ldg(p.field_scale + 2 * (p.t0 + t) + 1);
+    }
+    ColumnC cc;
+    double r0;
+    if (MODE == MHB200_METHOD_BC05) {
+      const double* rt = p.ring_tab + h;
+      const double N = __ldg(rt + 2 * p.nlat), N1 = __ldg(rt + 3 * p.nlat);
+      const double gs = __ldg(rt + 6 * p.nlat), c1 = __ldg(rt + 7 * p.nlat);
+      cc.a1 = __ldg(rt) * sg;
+      cc.a2 = __ldg(rt + p.nlat) * (sg * sg);
+      cc.st = __ldg(rt + 4 * p.nlat);
+      cc.ct = __ldg(rt + 5 * p.nlat);
+      cc.g0 = gs;
+      cc.g1 = -(gs * c1) * p.inv_rad;
+      cc.g2 = (3.0 * gs) * (p.inv_rad * p.inv_rad);
+      const double ex = N * cc.st, ez = N1 * cc.ct;
+      r0 = sqrt(fma(ez, ez, ex * ex)) * p.inv_rad + p.hc * p.inv_rad;
+      cc.cinv = 1.0 / (p.rad_e * r0);
+      cc.NG = N + geo;
+      cc.NG1 = N1 + geo;
+      cc.rad_e = cc.sg = cc.inv_r0 = cc.c0 = 0.0;
+    } else {
+      r0 = 1.0 + p.hc * p.inv_rad;
+      cc.rad_e = p.rad_e;
+      cc.sg = sg;
+      cc.inv_r0 = 1.0 / r0;
+      cc.c0 = fma(geo * p.inv_rad, cc.inv_r0, -1.0);
+      cc.a1 = cc.a2 = cc.st = cc.ct = cc.g0 = cc.g1 = cc.g2 = cc.NG = cc.NG1 = cc.cinv = 0.0;
+    }
+
+    double acc[NMOMC];
+#pragma unroll
+    for (int j = 0; j < NMOMC; ++j) acc[j] = 0.0;
+
+    for (int g = 0; g < ngroups; ++g, ++item) {
+      issue(item + MSTAGES - 1);
+      const int s = item % MSTAGES;
+      mbar_wait(&full[s], (item / MSTAGES) & 1);
+      const Tin* zs = stages + (size_t)s * STAGE_ELEMS + sub * MLG * MKCF + pos;
+      const Tin* ps = zs + 4 * MLG * MKCF;
+      const int nl = min(MLG, p.nlev - g * MLG);
+      double z[MLG], dpv[MLG];
+#pragma unroll
+      for (int k = 0; k < MLG; ++k) {
+        z[k] = (k < nl) ? (double)zs[k * MKCF] : 0.0;
+        dpv[k] = (k < nl) ? (double)ps[k * MKCF] : 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (active) {
+        if (nl == MLG) {
+          moment_levels<MODE, MLG>(z, dpv, cc, acc, p.dbound_hi, viol);
+        } else {
+          // tail group (nlev % 4 levels): no padded work
+          if (nl & 2) {
+            const double z2[2] = {z[0], z[1]}, d2[2] = {dpv[0], dpv[1]};
+            moment_levels<MODE, 2>(z2, d2, cc, acc, p.dbound_hi, viol);
+          }
+          if (nl & 1) {
+            const double z1[1] = {(nl & 2) ? z[2] : z[0]}, d1[1] = {(nl & 2) ? dpv[2] : dpv[0]};
+            moment_levels<MODE, 1>(z1, d1, cc, acc, p.dbound_hi, viol);
+          }
+        }
+      }
+    }
+
+    // first trig fragments of this chunk (L2 latency hides behind the fold) and next unit's column
+    const double* Ablk = p.trig + ((size_t)(c * 16) * 16 + (par * 4 + gi) * 2) * 32 + lane;
+    double ac[4], as[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ac[i] = __ldg(Ablk + i * 512);
+      as[i] = __ldg(Ablk + i * 512 + 32);
+    }
+    if (u + 1 < u_end) column_of(u + 1, col_next, geo_next);
+
+    // fold over the four symmetric columns (phi, -phi, pi - phi, pi + phi), held by the lanes sub = 0..3 of
+    // this warp: lane sub = v ends up with fold variant v (0 even-order cosine, 1 even sine, 2 odd cosine,
+    // 3 odd sine; see fold_chunk in stokes_grid.cu)
+#pragma unroll
+    for (int j = 0; j < NMOMC; ++j) {
+      double x = acc[j];
+      const double y = __shfl_xor_sync(0xffffffffu, x, 8);
+      x = (sub & 1) ? (y - x) : (x + y);
+      const double zz = __shfl_xor_sync(0xffffffffu, x, 16);
+      acc[j] = (sub == 1) ? (x - zz) : (sub == 2) ? (zz - x) : (x + zz);
+    }
+    // every warp has finished the previous chunk's contraction (reads of Mf)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    {
+      double* dst = Mf + sub * MF_V + (jj >> 2) * MF_KS + (jj & 3);
+#pragma unroll
+      for (int j = 0; j < NMOMC; ++j) dst[(j >> 3) * 32 + (j & 7) * 4] = acc[j];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    // contraction of the chunk: rows = 8 orders of one parity (cos and sin tiles), k = 4 contraction
+    // columns, n = 8 moments; cosine rows read the variant 2*par, sine rows 2*par + 1
+    {
+      const double* Bc = Mf + (2 * par) * MF_V + lane;
+      const double* Bs = Bc + MF_V;
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        const double a_c = ac[ks & 3], a_s = as[ks & 3];
+        if (ks + 4 < 16) {
+          ac[ks & 3] = __ldg(Ablk + (ks + 4) * 512);
+          as[ks & 3] = __ldg(Ablk + (ks + 4) * 512 + 32);
+        }
+        const double b0 = Bc[ks * MF_KS], b1 = Bc[ks * MF_KS + 32];
+        const double b2 = Bs[ks * MF_KS], b3 = Bs[ks * MF_KS + 32];
+        dmma884(facc[0][0][0], facc[0][0][1], a_c, b0);
+        dmma884(facc[0][1][0], facc[0][1][1], a_c, b1);
+        dmma884(facc[1][0][0], facc[1][0][1], a_s, b2);
+        dmma884(facc[1][1][0], facc[1][1][1], a_s, b3);
+      }
+    }
+
+    if (c == nchunks - 1 || u == u_end - 1) {
+      // end of this CTA's part of ring h: flush the Fourier sums (sign of einsum(m_phi, -pfactor), :270)
+      const double scale = (MODE == MHB200_METHOD_BC05) ? -sp : -sp / 9.80665;
+      const int m = 16 * gi + 2 * (lane >> 2) + par;
+      double* Fs = p.F + ((size_t)slot * MBLK + m) * 32 + 2 * (lane & 3);
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          *reinterpret_cast<double2*>(Fs + cs * 16 + nt * 8) =
+              make_double2(facc[cs][nt][0] * scale, facc[cs][nt][1] * scale);
+          facc[cs][nt][0] = facc[cs][nt][1] = 0.0;
+        }
+      if (tid == 0) {
+        p.slot_r0[slot] = r0;
+        p.slot_ring[slot] = h;
+      }
+      ++slot;
+    }
+  }
+  if (__syncthreads_or(viol) && tid == 0) atomicOr(p.flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_B: Legendre sum over the slots, per (degree block, order), as DMMA tiles
+//   rows = (cs, moment) 32 = 4 row tiles (one per warp), k = 4 slots, n = 8 degrees
+// The weighted P_lm values of 128 slots x 16 degrees are generated by the Holmes-Featherstone recursion
+// (thread = slot; operation order of gravity_toolkit.plm_holmes as in legendre_ring of stokes_grid.cu)
+// into a fragment-major shared-memory tile, double buffered.
+// ------------------------------------------------------------------------------------------------
+struct LegParams {
+  int lmax, mmax, Mpad, Frows, nlb, noff, nsplit, nunits;
+  const int* unit_lm;          // [nunits][2]: degree block, order
+  const double *f1, *f2, *pmm, *sq, *rescale, *x, *w, *ckpt;
+  const double* F;
+  const double* slot_r0;
+  const int* slot_ring;
+  int field_slot[NB_SUB + 1];
+  double* G;
+  const int* flag;
+};
+
+__global__ void __launch_bounds__(128) legendre_moment_kernel(const __grid_constant__ LegParams q) {
+  if (*reinterpret_cast<const volatile int*>(q.flag) != 0) return;
+  __shared__ double tile[2][32 * 64];
+  const int unit = blockIdx.x, tt = blockIdx.y / q.nsplit, split = blockIdx.y % q.nsplit;
+  const int lb = q.unit_lm[2 * unit], m = q.unit_lm[2 * unit + 1];
+  const int lbase = lb * LBLK, lend = min(lbase + LBLK - 1, q.lmax);
+  const int sb = q.field_slot[tt], se = q.field_slot[tt + 1];
+  const int s0 = sb + (int)((long long)(se - sb) * split / q.nsplit);
+  const int s1 = sb + (int)((long long)(se - sb) * (split + 1) / q.nsplit);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int first_sub = max(0, m - lbase) >> 4;      // 16-degree sub-blocks wholly below the diagonal are skipped
+  const int nsub = ((lend - lbase) >> 4) + 1;
+  const bool from_ckpt = (q.ckpt != nullptr && lb > 0 && m <= lbase - 2);
+  const double* f1 = q.f1 + m;
+  const double* f2 = q.f2 + m;
+  const double pmm = q.pmm[m], sqm = q.sq[m];
+
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+
+  for (int sblk = s0; sblk < s1; sblk += 128) {
+    // A fragments of the block: F[slot][m][(cs, j)], row tile = warp
+    double af[32];
+#pragma unroll
+    for (int ks = 0; ks < 32; ++ks) {
+      const int s = sblk + 4 * ks + (lane & 3);
+      af[ks] = (s < s1) ? __ldg(q.F + ((size_t)s * q.Frows + m) * 32 + warp * 8 + (lane >> 2)) : 0.0;
+    }
+    const int s = sblk + tid;
+    const bool valid = (s < s1);
+    const int h = valid ? q.slot_ring[s] : 0;
+    const double rho = valid ? q.slot_r0[s] : 1.0;
+    const double xv = q.x[h], wh = q.w[h];
+    const double rs = q.rescale[(size_t)h * q.Mpad + m];
+    // recursion state: (p2, p1) = values at degrees (l - 2, l - 1) for the next degree l
+    double p2 = 0.0, p1 = 0.0;
+    int lnext;                          // next degree the recursion produces
+    if (from_ckpt) {
+      const double* ck = q.ckpt + (((size_t)h * q.nlb + lb) * q.Mpad + m) * 2;
+      p2 = ck[0];
+      p1 = ck[1];
+      lnext = lbase;
+    } else {
+      lnext = m;                        // sectoral seed first (may lie one degree below the block)
+    }
+    auto step = [&]() -> double {        // produces degree lnext
+      double cur;
+      if (lnext == m) {
+        cur = pmm;
+      } else if (lnext == m + 1) {
+        cur = __dmul_rn(__dmul_rn(xv, sqm), p1);
+      } else {
+        cur = __dsub_rn(__dmul_rn(__dmul_rn(xv, __ldg(f1 + (size_t)lnext * q.Mpad)), p1),
+                        __dmul_rn(__ldg(f2 + (size_t)lnext * q.Mpad), p2));
+      }
+      p2 = p1;
+      p1 = cur;
+      ++lnext;
+      return cur;
+    };
+    while (lnext < lbase + 16 * first_sub && lnext < m + 2 && lnext <= lend) step();   // at most the seed degree
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      if (sub >= first_sub && sub < nsub) {
+        double* T = tile[sub & 1];
+        const int l0 = lbase + 16 * sub;
+        double rp = ipow(rho, max(l0, m) + q.noff);
+        const int ks = tid >> 2, k = tid & 3;
+#pragma unroll
+        for (int dl = 0; dl < 16; ++dl) {
+          const int l = l0 + dl;
+          double v = 0.0;
+          if (l >= m && l <= lend) {
+            const double cur = step();
+            v = __dmul_rn(__dmul_rn(cur, rs), wh) * rp;
+            rp *= rho;
+          }
+          T[ks * 64 + (dl >> 3) * 32 + ((((dl & 7) + ks) & 7) << 2) + k] = valid ? v : 0.0;
+        }
+        __syncthreads();
+        const double* Tb = T + (lane & 3);
+        const int n = lane >> 2;
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          const double b0 = Tb[kk * 64 + (((n + kk) & 7) << 2)];
+          const double b1 = Tb[kk * 64 + 32 + (((n + kk) & 7) << 2)];
+          dmma884(acc[2 * sub][0], acc[2 * sub][1], af[kk], b0);
+          dmma884(acc[2 * sub + 1][0], acc[2 * sub + 1][1], af[kk], b1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  double* Gd = q.G + (((size_t)(tt * q.nsplit + split) * q.nunits + unit) * 4 + warp) * 512 + lane * 2;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(Gd + nt * 64) = make_double2(acc[nt][0], acc[nt][1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_C: binomial expansion + degree factors:  C_lm = dfactor[l] sum_j C(l + n0, j) sum_split G
+// ------------------------------------------------------------------------------------------------
+struct FinParams {
+  int lmax, mmax, nsplit, nunits;
+  const int* lb_unit0;         // first unit of every degree block
+  const double* E;             // [16][lmax + 1] binomial coefficients C(l + n0, j)
+  const double* G;
+  double *clm, *slm;
+  const int* flag;
+  const double* dfactor_dev;   // used when lmax + 1 > 448
+  double dfactor[448];
+};
+
+__global__ void __launch_bounds__(64) moment_finalize_kernel(const __grid_constant__ FinParams q) {
+  if (*reinterpret_cast<const volatile int*>(q.flag) != 0) return;
+  const int l = blockIdx.x, tt = blockIdx.y;
+  const double df = (q.dfactor_dev != nullptr) ? q.dfactor_dev[l] : q.dfactor[l];
+  const int nt = (l & 63) >> 3, ll = (l & 7) >> 1, e = l & 1;
+  for (int m = threadIdx.x; m <= q.mmax; m += blockDim.x) {
+    double c = 0.0, s = 0.0;
+    if (m <= l) {
+      const int unit = q.lb_unit0[l >> 6] + m;
+      for (int sp = 0; sp < q.nsplit; ++sp) {
+        const double* g = q.G + ((size_t)(tt * q.nsplit + sp) * q.nunits + unit) * G_UNIT + nt * 64 + ll * 2 + e;
+        double cc = 0.0, ss = 0.0;
+#pragma unroll
+        for (int j = NMOMC - 1; j >= 0; --j) {          // small terms first
+          const double ej = __ldg(q.E + (size_t)j * (q.lmax + 1) + l);
+          const int o = (j >> 3) * 512 + (j & 7) * 8;   // row tile j / 8 (+2 for sine), lane (j % 8) * 4 + ll
+          cc = fma(ej, g[o], cc);
+          ss = fma(ej, g[o + 1024], ss);
+        }
+        c += cc;
+        s += ss;
+      }
+    }
+    const size_t o = ((size_t)tt * (q.lmax + 1) + l) * (q.mmax + 1) + m;
+    q.clm[o] = c * df;
+    q.slm[o] = s * df;
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct MomSchedule {
+  int nb = 0, h0 = 0, h1 = 0, ncta = 0, nslots = 0;
+  int* cta_unit_dev = nullptr;
+  int* cta_slot_dev = nullptr;
+  std::vector<int> field_slot;          // [nb + 1]
+};
+
+struct MomentPlan {
+  bool tma_ok = false;                  // the fold sub-blocks of every chunk are contiguous longitude runs
+  int nchunks = 0, nf = 0, nunits = 0, ncta_max = 0;
+  int dir[4] = {1, 1, 1, 1};
+  int *box_start = nullptr, *col_grid = nullptr, *unit_lm = nullptr, *lb_unit0 = nullptr;
+  double* trig = nullptr;               // [nmb][nchunks * 16][16][32]
+  double* E = nullptr;                  // [2][16][lmax + 1]: n0 = 2, n0 = 4
+  std::vector<MomSchedule> sched;
+};
+
+namespace {
+
+template <typename T>
+int upload_vec(T** dev, const std::vector<T>& host) {
+  MHB_CUDA(cudaMalloc((void**)dev, std::max<size_t>(host.size(), 1) * sizeof(T)));
+  if (!host.empty()) MHB_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MHB200_OK;
+}
+
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// layout of the moment region of a workspace
+struct MomWs {
+  size_t flag, slot_r0, slot_ring, F, G, total;
+};
+MomWs mom_layout(const mhb200_plan* pl, size_t max_slots, size_t g_units) {
+  MomWs w;
+  size_t o = 0;
+  w.flag = o;
+  o += 256;
+  w.slot_r0 = o;
+  o = align256(o + max_slots * sizeof(double));
+  w.slot_ring = o;
+  o = align256(o + max_slots * sizeof(int));
+  w.F = o;
+  o = align256(o + max_slots * (size_t)pl->Mpad * 32 * sizeof(double));
+  w.G = o;
+  o = align256(o + g_units * G_UNIT * sizeof(double));
+  w.total = o;
+  return w;
+}
+
+int pick_nsplit(const mhb200_plan* pl, int nb) {
+  const int want = (2 * pl->num_sms + nb * pl->mom->nunits - 1) / (nb * pl->mom->nunits);
+  return std::max(1, std::min(MAX_SPLIT, want));
+}
+
+size_t g_units_bound(const mhb200_plan* pl, int nb_max) {
+  size_t best = 0;
+  for (int nb = 1; nb <= nb_max; ++nb)
+    best = std::max(best, (size_t)nb * pick_nsplit(pl, nb) * pl->mom->nunits);
+  return best;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// 4-D map (lon, lat, level, field) of a (field, level, lat, lon) cube; box = 64 lon x 1 lat x MLG levels
+int make_cube_map(CUtensorMap* tm, const void* base, int dtype, int nlon, int nlat, int nlev, int nfields,
+                  long long batch_stride) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) {
+    set_err("cuTensorMapEncodeTiled is not available from the driver");
+    return MHB200_ECUDA;
+  }
+  const size_t esz = (dtype == MHB200_F64) ? 8 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)nlon, (cuuint64_t)nlat, (cuuint64_t)nlev, (cuuint64_t)std::max(nfields, 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)nlon * esz, (cuuint64_t)nlon * nlat * esz,
+                           (cuuint64_t)(nfields > 1 ? batch_stride : (long long)nlon * nlat * nlev) * esz};
+  cuuint32_t box[4] = {(cuuint32_t)MKCF, 1, (cuuint32_t)MLG, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, dtype == MHB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return MHB200_ECUDA;
+  }
+  return MHB200_OK;
+}
+
+MomSchedule* get_schedule(mhb200_plan* pl, int nb, int h0, int h1, int* rc_out) {
+  MomentPlan* mp = pl->mom;
+  *rc_out = MHB200_OK;
+  for (auto& s : mp->sched)
+    if (s.nb == nb && s.h0 == h0 && s.h1 == h1) return &s;
+  MomSchedule sc;
+  sc.nb = nb;
+  sc.h0 = h0;
+  sc.h1 = h1;
+  std::vector<int> cta_unit, cta_slot, field_slot;
+  sc.ncta = moment_schedule(nb, h1 - h0, mp->nchunks, mp->ncta_max, cta_unit, cta_slot, field_slot, &sc.nslots);
+  sc.field_slot = field_slot;
+  int rc;
+  if ((rc = upload_vec(&sc.cta_unit_dev, cta_unit)) != MHB200_OK || (rc = upload_vec(&sc.cta_slot_dev, cta_slot)) != MHB200_OK) {
+    *rc_out = rc;
+    return nullptr;
+  }
+  mp->sched.push_back(sc);
+  return &mp->sched.back();
+}
+
+}  // namespace
+
+// Equal split of the linearised (field, ring, chunk) units over the CTAs; a slot is the part of one ring a
+// CTA owns.  Pure host logic (exposed to the CPU tests through mhb200_moment_schedule_probe).
+int moment_schedule(int nb, int nrings, int nchunks, int max_ctas, std::vector<int>& cta_unit,
+                    std::vector<int>& cta_slot, std::vector<int>& field_slot, int* nslots) {
+  const long long units = (long long)nb * nrings * nchunks;
+  const int ncta = (int)std::min<long long>(max_ctas, units);
+  cta_unit.assign(ncta + 1, 0);
+  cta_slot.assign(ncta, 0);
+  field_slot.assign(nb + 1, 0);
+  for (int b = 0; b <= ncta; ++b) cta_unit[b] = (int)(units * b / ncta);
+  int slot = 0, last_field = -1;
+  for (int b = 0; b < ncta; ++b) {
+    cta_slot[b] = slot;
+    long long prev_ring = -1;
+    for (int u = cta_unit[b]; u < cta_unit[b + 1]; ++u) {
+      const long long ring = u / nchunks;          // (field, ring) linearised
+      if (ring != prev_ring) {
+        const int t = (int)(ring / nrings);
+        while (last_field < t) field_slot[++last_field] = slot;
+        ++slot;
+        prev_ring = ring;
+      }
+    }
+  }
+  while (last_field < nb) field_slot[++last_field] = slot;
+  *nslots = slot;
+  return ncta;
+}
+
+int moment_plan_create(mhb200_plan* pl, const double* phi) {
+  pl->mom = nullptr;
+  if (pl->fold != 2) return MHB200_OK;
+  MomentPlan* mp = new MomentPlan();
+  pl->mom = mp;
+  const int nf = (int)pl->colp.size();
+  mp->nf = nf;
+  mp->nchunks = (nf + MKCF - 1) / MKCF;
+  mp->ncta_max = 2 * pl->num_sms;
+  const std::vector<int>* sets[4] = {&pl->colp, &pl->colq, &pl->colp2, &pl->colq2};
+  // thread column (warp, lane) of chunk c: sub = lane / 8, contraction column j = 64 c + 8 warp + lane % 8.
+  // A grid column that appears in two sub-blocks of the same contraction column (phi = 0, pi, +-pi/2) is
+  // kept in the first and dropped from the others, so every trig entry has weight 1.
+  std::vector<int> col_grid((size_t)mp->nchunks * MKC, -1), box_start((size_t)mp->nchunks * 4, 0);
+  auto column = [&](int sb, int j) -> int {
+    if (j >= nf) return -1;
+    const int col = (*sets[sb])[j];
+    for (int s2 = 0; s2 < sb; ++s2)
+      if ((*sets[s2])[j] == col) return -1;
+    return col;
+  };
+  // direction of every sub-block's run (from the first two contraction columns that are both kept)
+  bool ok = true;
+  for (int sb = 0; sb < 4; ++sb) {
+    int dir = 0;
+    for (int j = 0; j + 1 < nf && dir == 0; ++j) {
+      const int a = column(sb, j), b = column(sb, j + 1);
+      if (a >= 0 && b >= 0) dir = b - a;
+    }
+    if (dir == 0) dir = 1;                       // a single column
+    if (dir != 1 && dir != -1) ok = false;
+    mp->dir[sb] = (dir < 0) ? -1 : 1;
+  }
+  for (int c = 0; c < mp->nchunks; ++c)
+    for (int sb = 0; sb < 4; ++sb) {
+      bool have = false;
+      int start = 0;
+      for (int jj = 0; jj < MKCF; ++jj) {
+        const int col = column(sb, c * MKCF + jj);
+        const int warp = jj >> 3, lane = sb * 8 + (jj & 7);
+        col_grid[(size_t)c * MKC + warp * 32 + lane] = col;
+        if (col < 0) continue;
+        const int pos = (mp->dir[sb] > 0) ? jj : (MKCF - 1 - jj);
+        if (!have) {
+          start = col - pos;
+          have = true;
+        } else if (col - pos != start) {
+          ok = false;
+        }
+      }
+      box_start[(size_t)c * 4 + sb] = have ? start : 0;
+    }
+  mp->tma_ok = ok;
+  // trig table (m_phi of gen_pressure_stokes.py:176-177 on the contraction columns), fragment-major:
+  // row tile (par*4 + gi)*2 + {cos, sin}, row r: order 64 mb + 16 gi + 2 r + par; k: column 4 ks + lane % 4
+  const int nks = mp->nchunks * 16;
+  std::vector<double> trig((size_t)pl->nmb * nks * 512, 0.0);
+  for (int mb = 0; mb < pl->nmb; ++mb)
+    for (int ks = 0; ks < nks; ++ks)
+      for (int g = 0; g < 8; ++g)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int par = g >> 2, gi = g & 3;
+          const int m = mb * MBLK + 16 * gi + 2 * (lane >> 2) + par;
+          const int j = ks * 4 + (lane & 3);
+          if (m > pl->mmax || j >= nf) continue;
+          const double arg = (double)m * phi[pl->colp[j]];
+          const size_t base = (((size_t)mb * nks + ks) * 16 + g * 2) * 32 + lane;
+          trig[base] = cos(arg);
+          trig[base + 32] = sin(arg);
+        }
+  // K_B units: (degree block, order), orders 0 .. min(64 lb + 63, mmax)
+  std::vector<int> unit_lm, lb_unit0(pl->nlb, 0);
+  for (int lb = 0; lb < pl->nlb; ++lb) {
+    lb_unit0[lb] = (int)unit_lm.size() / 2;
+    for (int m = 0; m <= std::min(lb * LBLK + LBLK - 1, pl->mmax); ++m) {
+      unit_lm.push_back(lb);
+      unit_lm.push_back(m);
+    }
+  }
+  mp->nunits = (int)unit_lm.size() / 2;
+  // binomial coefficients C(l + n0, j), n0 = 2 (BC05, pressure) and 4 (SW02)
+  const int nl = pl->lmax + 1;
+  std::vector<double> E((size_t)2 * NMOMC * nl, 0.0);
+  for (int v = 0; v < 2; ++v)
+    for (int l = 0; l < nl; ++l) {
+      const int n = l + (v ? 4 : 2);
+      long double cnj = 1.0L;
+      for (int j = 0; j < NMOMC; ++j) {
+        if (j > 0) cnj = cnj * (long double)(n - j + 1) / (long double)j;
+        E[((size_t)v * NMOMC + j) * nl + l] = (j <= n) ? (double)cnj : 0.0;
+      }
+    }
+  int rc;
+  if ((rc = upload_vec(&mp->col_grid, col_grid)) || (rc = upload_vec(&mp->box_start, box_start)) ||
+      (rc = upload_vec(&mp->trig, trig)) || (rc = upload_vec(&mp->unit_lm, unit_lm)) ||
+      (rc = upload_vec(&mp->lb_unit0, lb_unit0)) || (rc = upload_vec(&mp->E, E)))
+    return rc;
+  return MHB200_OK;
+}
+
+void moment_plan_destroy(mhb200_plan* pl) {
+  MomentPlan* mp = pl->mom;
+  if (!mp) return;
+  cudaFree(mp->box_start);
+  cudaFree(mp->col_grid);
+  cudaFree(mp->unit_lm);
+  cudaFree(mp->lb_unit0);
+  cudaFree(mp->trig);
+  cudaFree(mp->E);
+  for (auto& s : mp->sched) {
+    cudaFree(s.cta_unit_dev);
+    cudaFree(s.cta_slot_dev);
+  }
+  delete mp;
+  pl->mom = nullptr;
+}
+
+// bytes of the moment region for calls with up to nb_max fields per launch and `launches` K_A launches
+size_t moment_workspace_bytes(const mhb200_plan* pl, int nbatch, int launches) {
+  if (!pl->mom) return 0;
+  const int nb = std::min(nbatch, NB_SUB);
+  const size_t max_slots = (size_t)nb * pl->nlat + (size_t)launches * pl->mom->ncta_max;
+  return mom_layout(pl, max_slots, g_units_bound(pl, nb)).total;
+}
+
+static int moment_mode_env() {
+  // MHB200_MOMENTS: 0 direct powers, 1 moments expanded before the Fourier sum (stokes_grid.cu),
+  // 2 (default) contracted moments (this file)
+  if (const char* e = getenv("MHB200_MOMENTS")) return atoi(e);
+  return 2;
+}
+
+bool moment_atm_eligible(const mhb200_plan* pl, int dtype, const void* GPH, const void* dP, long long batch_stride,
+                         int nbatch, const double* plm_table) {
+  const MomentPlan* mp = pl->mom;
+  if (!mp || !mp->tma_ok || pl->nlb != 1 || plm_table != nullptr || moment_mode_env() < 2) return false;
+  if (!tensor_map_encoder()) return false;
+  const size_t esz = (dtype == MHB200_F64) ? 8 : 4;
+  if (((uintptr_t)GPH | (uintptr_t)dP) & 15) return false;
+  if (((size_t)pl->nlon * esz) % 16) return false;
+  if (nbatch > 1 && batch_stride != 0 && ((size_t)batch_stride * esz) % 16) return false;
+  return true;
+}
+
+struct MomCall {
+  int mode, dtype, nlev;
+  const void *GPH, *dP;
+  long long batch_stride;
+  const double* field_scale_dev;
+  const double* geoid;
+  long long geo_s0, geo_s1;
+  const double* ring_tab;
+  double rad_e;
+};
+
+static int launch_atm_kernel(const MomCall& c, const CUtensorMap& tz, const CUtensorMap& tp, const AtmMomParams& ap,
+                             int ncta, cudaStream_t st) {
+  const size_t esz = (c.dtype == MHB200_F64) ? 8 : 4;
+  const size_t smem = (size_t)MSTAGES * 2 * 4 * MLG * MKCF * esz + 4 * MF_V * sizeof(double) + 2 * MSTAGES * 8;
+#define MHB_LAUNCH_ATM(MODE, T)                                                                              \
+  do {                                                                                                       \
+    auto kern = atm_moment_kernel<MODE, T>;                                                                  \
+    MHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    profile_begin(st);                                                                                       \
+    kern<<<ncta, 256, smem, st>>>(tz, tp, ap);                                                               \
+    profile_end(st);                                                                                         \
+  } while (0)
+  if (c.mode == MHB200_METHOD_BC05) {
+    if (c.dtype == MHB200_F64) MHB_LAUNCH_ATM(MHB200_METHOD_BC05, double);
+    else MHB_LAUNCH_ATM(MHB200_METHOD_BC05, float);
+  } else {
+    if (c.dtype == MHB200_F64) MHB_LAUNCH_ATM(MHB200_METHOD_SW02, double);
+    else MHB_LAUNCH_ATM(MHB200_METHOD_SW02, float);
+  }
+#undef MHB_LAUNCH_ATM
+  g_launches.fetch_add(1);
+  MHB_CUDA(cudaGetLastError());
+  return MHB200_OK;
+}
+
+// K_A for fields [t0, t0 + nb) and rings [h0, h1); slots start at slot_base.  *nslots_out = slots written.
+static int moment_atm_launch(mhb200_plan* pl, const MomCall& c, const MomWs& lay, char* ws, int t0, int nb, int h0,
+                             int h1, int slot_base, MomSchedule** sched_out, cudaStream_t st) {
+  MomentPlan* mp = pl->mom;
+  int rc;
+  MomSchedule* sc = get_schedule(pl, nb, h0, h1, &rc);
+  if (!sc) return rc;
+  *sched_out = sc;
+  const size_t esz = (c.dtype == MHB200_F64) ? 8 : 4;
+  const bool shared = (c.batch_stride == 0);
+  const char* gbase = (const char*)c.GPH + (shared ? 0 : (size_t)t0 * c.batch_stride * esz);
+  const char* pbase = (const char*)c.dP + (shared ? 0 : (size_t)t0 * c.batch_stride * esz);
+  CUtensorMap tz, tp;
+  const int nf_map = shared ? 1 : nb;
+  if ((rc = make_cube_map(&tz, gbase, c.dtype, pl->nlon, pl->nlat, c.nlev, nf_map, c.batch_stride)) != MHB200_OK) return rc;
+  if ((rc = make_cube_map(&tp, pbase, c.dtype, pl->nlon, pl->nlat, c.nlev, nf_map, c.batch_stride)) != MHB200_OK) return rc;
+  AtmMomParams ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.nlat = pl->nlat;
+  ap.nlon = pl->nlon;
+  ap.nlev = c.nlev;
+  ap.nchunks = mp->nchunks;
+  ap.ngroups = (c.nlev + MLG - 1) / MLG;
+  ap.h0 = h0;
+  ap.nrings = h1 - h0;
+  ap.t0 = t0;
+  ap.fields_in_map = nf_map;
+  ap.cta_unit = sc->cta_unit_dev;
+  ap.cta_slot = sc->cta_slot_dev;
+  ap.slot_base = slot_base;
+  ap.box_start = mp->box_start;
+  ap.col_grid = mp->col_grid;
+  for (int i = 0; i < 4; ++i) ap.dir[i] = mp->dir[i];
+  ap.ring_tab = c.ring_tab;
+  ap.geoid = c.geoid;
+  ap.geo_s0 = c.geo_s0;
+  ap.geo_s1 = c.geo_s1;
+  ap.field_scale = c.field_scale_dev;
+  ap.trig = mp->trig;
+  ap.F = (double*)(ws + lay.F);
+  ap.slot_r0 = (double*)(ws + lay.slot_r0);
+  ap.slot_ring = (int*)(ws + lay.slot_ring);
+  ap.flag = (int*)(ws + lay.flag);
+  ap.rad_e = c.rad_e;
+  ap.inv_rad = 1.0 / c.rad_e;
+  ap.hc = MOM_CENTER_HEIGHT;
+  const int noff = (c.mode == MHB200_METHOD_BC05) ? 2 : 4;
+  const double bound = MOM_ND_BOUND / (double)(pl->lmax + noff);
+  unsigned long long bits;
+  memcpy(&bits, &bound, 8);
+  ap.dbound_hi = (unsigned)(bits >> 32);
+  return launch_atm_kernel(c, tz, tp, ap, sc->ncta, st);
+}
+
+// K_B + K_C over the slots described by field_slot[0..nb]
+static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, const int* field_slot, int noff,
+                         const double* dfactor, const double* dfactor_dev, double* clm, double* slm,
+                         cudaStream_t st) {
+  MomentPlan* mp = pl->mom;
+  const int nsplit = pick_nsplit(pl, nb);
+  LegParams q;
+  memset(&q, 0, sizeof(q));
+  q.lmax = pl->lmax;
+  q.mmax = pl->mmax;
+  q.Mpad = pl->Mpad;
+  q.Frows = pl->Mpad;
+  q.nlb = pl->nlb;
+  q.noff = noff;
+  q.nsplit = nsplit;
+  q.nunits = mp->nunits;
+  q.unit_lm = mp->unit_lm;
+  q.f1 = pl->f1;
+  q.f2 = pl->f2;
+  q.pmm = pl->pmm;
+  q.sq = pl->sq;
+  q.rescale = pl->rescale;
+  q.x = pl->x;
+  q.w = pl->w;
+  q.ckpt = pl->ckpt;
+  q.F = (const double*)(ws + lay.F);
+  q.slot_r0 = (const double*)(ws + lay.slot_r0);
+  q.slot_ring = (const int*)(ws + lay.slot_ring);
+  for (int i = 0; i <= nb; ++i) q.field_slot[i] = field_slot[i];
+  q.G = (double*)(ws + lay.G);
+  q.flag = (const int*)(ws + lay.flag);
+  legendre_moment_kernel<<<dim3(mp->nunits, nb * nsplit), 128, 0, st>>>(q);
+  g_launches.fetch_add(1);
+  MHB_CUDA(cudaGetLastError());
+  FinParams f;
+  f.lmax = pl->lmax;
+  f.mmax = pl->mmax;
+  f.nsplit = nsplit;
+  f.nunits = mp->nunits;
+  f.lb_unit0 = mp->lb_unit0;
+  f.E = mp->E + (noff == 4 ? (size_t)NMOMC * (pl->lmax + 1) : 0);
+  f.G = q.G;
+  f.clm = clm;
+  f.slm = slm;
+  f.flag = q.flag;
+  f.dfactor_dev = dfactor_dev;
+  if (!dfactor_dev)
+    for (int l = 0; l <= pl->lmax; ++l) f.dfactor[l] = dfactor[l];
+  moment_finalize_kernel<<<dim3(pl->lmax + 1, nb), 64, 0, st>>>(f);
+  g_launches.fetch_add(1);
+  MHB_CUDA(cudaGetLastError());
+  return MHB200_OK;
+}
+
+// Device-resident cubes, all rings: sub-batches of NB_SUB fields through K_A, K_B, K_C.
+// `mom_ws` is the moment region of the caller's workspace; *flag_out = device flag the fallback reads.
+int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const void* dP, long long batch_stride,
+                   const double* field_scale_dev, const double* geoid, long long geo_s0, long long geo_s1,
+                   const double* ring_tab, int nlev, int nbatch, double rad_e, const double* dfactor,
+                   double* clm, double* slm, void* mom_ws, const int** flag_out, cudaStream_t st) {
+  const int nbmax = std::min(nbatch, NB_SUB);
+  const MomWs lay = mom_layout(pl, (size_t)nbmax * pl->nlat + pl->mom->ncta_max, g_units_bound(pl, nbmax));
+  char* ws = (char*)mom_ws;
+  MHB_CUDA(cudaMemsetAsync(ws + lay.flag, 0, sizeof(int), st));
+  *flag_out = (const int*)(ws + lay.flag);
+  MomCall c;
+  c.mode = mode;
+  c.dtype = dtype;
+  c.nlev = nlev;
+  c.GPH = GPH;
+  c.dP = dP;
+  c.batch_stride = batch_stride;
+  c.field_scale_dev = field_scale_dev;
+  c.geoid = geoid;
+  c.geo_s0 = geo_s0;
+  c.geo_s1 = geo_s1;
+  c.ring_tab = ring_tab;
+  c.rad_e = rad_e;
+  const size_t nout = (size_t)(pl->lmax + 1) * (pl->mmax + 1);
+  const int noff = (mode == MHB200_METHOD_BC05) ? 2 : 4;
+  for (int t0 = 0; t0 < nbatch; t0 += NB_SUB) {
+    const int nb = std::min(NB_SUB, nbatch - t0);
+    MomSchedule* sc = nullptr;
+    int rc = moment_atm_launch(pl, c, lay, ws, t0, nb, 0, pl->nlat, 0, &sc, st);
+    if (rc != MHB200_OK) return rc;
+    rc = moment_reduce(pl, lay, ws, nb, sc->field_slot.data(), noff, dfactor, nullptr, clm + t0 * nout,
+                       slm + t0 * nout, st);
+    if (rc != MHB200_OK) return rc;
+  }
+  return MHB200_OK;
+}
+
+// Host-band path: one field, K_A per latitude band (as its H2D copy lands), one K_B/K_C at the end.
+int moment_band_begin(mhb200_plan* pl, int nbands, void* mom_ws, const int** flag_out, cudaStream_t st) {
+  const MomWs lay = mom_layout(pl, (size_t)pl->nlat + (size_t)nbands * pl->mom->ncta_max, g_units_bound(pl, 1));
+  MHB_CUDA(cudaMemsetAsync((char*)mom_ws + lay.flag, 0, sizeof(int), st));
+  *flag_out = (const int*)((char*)mom_ws + lay.flag);
+  return MHB200_OK;
+}
+
+int moment_band_launch(mhb200_plan* pl, int nbands, int mode, int dtype, const void* GPH, const void* dP,
+                       const double* geoid, long long geo_s0, long long geo_s1, const double* ring_tab, int nlev,
+                       double rad_e, int h0, int h1, int* slot_base, void* mom_ws, cudaStream_t st) {
+  const MomWs lay = mom_layout(pl, (size_t)pl->nlat + (size_t)nbands * pl->mom->ncta_max, g_units_bound(pl, 1));
+  MomCall c;
+  c.mode = mode;
+  c.dtype = dtype;
+  c.nlev = nlev;
+  c.GPH = GPH;
+  c.dP = dP;
+  c.batch_stride = 0;
+  c.field_scale_dev = nullptr;
+  c.geoid = geoid;
+  c.geo_s0 = geo_s0;
+  c.geo_s1 = geo_s1;
+  c.ring_tab = ring_tab;
+  c.rad_e = rad_e;
+  MomSchedule* sc = nullptr;
+  const int rc = moment_atm_launch(pl, c, lay, (char*)mom_ws, 0, 1, h0, h1, *slot_base, &sc, st);
+  if (rc != MHB200_OK) return rc;
+  *slot_base += sc->nslots;
+  return MHB200_OK;
+}
+
+int moment_band_finish(mhb200_plan* pl, int nbands, int mode, int nslots, const double* dfactor, double* clm,
+                       double* slm, void* mom_ws, cudaStream_t st) {
+  const MomWs lay = mom_layout(pl, (size_t)pl->nlat + (size_t)nbands * pl->mom->ncta_max, g_units_bound(pl, 1));
+  const int field_slot[2] = {0, nslots};
+  return moment_reduce(pl, lay, (char*)mom_ws, 1, field_slot, (mode == MHB200_METHOD_BC05) ? 2 : 4, dfactor, nullptr,
+                       clm, slm, st);
+}
+
+}  // namespace mhb

@@ -36,7 +36,9 @@ def _to_device(a, device, dtype=torch.float64, keep_f32=False):
             pass
         elif arr.dtype != np.float64:
             arr = arr.astype(np.float64)
-        if not arr.flags.c_contiguous and arr.ndim < 2:
+        # torch.from_numpy rejects negative strides (lat-flipped views such as P[::-1, :], which the
+        # reference accepts); positive-stride views of 2-D+ operands stay views (addressed with strides)
+        if (not arr.flags.c_contiguous and arr.ndim < 2) or any(st < 0 for st in arr.strides):
             arr = np.ascontiguousarray(arr)
         t = torch.from_numpy(np.atleast_1d(arr)).to('cuda:%d' % device, non_blocking=True)
     if keep_f32 and t.dtype == torch.float32:

@@ -105,10 +105,14 @@ def clear_plans():
 
 def plm_table_for(plan, PLM, lmax, mmax):
     """
-    Decides how to honour a caller-supplied ``PLM`` (reference ``gen_pressure_stokes.py:180-188``).
-    ``MHB200_PLM_MODE``: ``auto`` (default) recomputes on the fly when the table matches the
-    standard Holmes-Featherstone values for ``lat`` at sampled entries, otherwise uploads and
-    uses the caller's table; ``table`` always uses the table; ``recompute`` never does.
+    Decides how to honour a caller-supplied ``PLM`` (reference ``gen_pressure_stokes.py:180-188``:
+    the reference always contracts with the table it is given).
+    ``MHB200_PLM_MODE``: ``auto`` (default) compares the WHOLE table ``PLM[:L+1, :M+1, :]`` with the
+    standard Holmes-Featherstone values for ``lat`` (host table cached per plan) and regenerates it on
+    the fly only when every entry agrees to 1e-12 of the table's scale -- otherwise the caller's table is
+    uploaded and used; ``table`` always uses the table; ``recompute`` never does.
+    The verdict is cached per (buffer address, shape, strides, strided content sample), so a driver that
+    passes the same array every time step pays for the comparison once.
     Returns None (on-the-fly recursion) or a (nlat, lmax+1, mmax+1) device tensor.
     """
     if PLM is None:
@@ -116,23 +120,30 @@ def plm_table_for(plan, PLM, lmax, mmax):
     mode = os.environ.get('MHB200_PLM_MODE', 'auto').lower()
     if mode == 'recompute':
         return None
-    # content fingerprint (strided sample), not object identity: addresses get reused
-    flat = np.asarray(PLM).reshape(-1)
+    arr = np.asarray(PLM)
+    flat = arr.reshape(-1)
     sample = np.ascontiguousarray(flat[::max(1, flat.size // 8192)], dtype=np.float64)
-    key = ('plm', hashlib.sha1(sample.tobytes()).hexdigest(), tuple(np.shape(PLM)), lmax, mmax)
+    key = ('plm', arr.__array_interface__['data'][0], arr.shape, arr.strides, str(arr.dtype),
+           hashlib.sha1(sample.tobytes()).hexdigest(), lmax, mmax, mode)
     with plan.lock:
         if key in plan.tables:
             return plan.tables[key]
     use_table = (mode == 'table')
     if not use_table:
-        samples = sorted(set([(0, 0), (min(1, lmax), 0), (lmax, 0), (lmax, min(mmax, lmax)),
-                              (lmax, min(mmax, lmax // 2)), (max(lmax // 2, min(mmax, 1)), min(mmax, 1))]))
-        samples = [(l, m) for (l, m) in samples if m <= l]
-        hs = sorted(set(int(v) for v in np.linspace(0, plan.nlat - 1, 7)))
-        ref = _compat.plm_columns(lmax, mmax, plan.costh[hs], samples)
-        got = np.array([[float(PLM[l, m, h]) for h in hs] for (l, m) in samples])
-        scale = np.maximum(np.abs(ref).max(), 1.0)
-        use_table = bool(np.abs(ref - got).max() > 1e-12 * scale)
+        skey = ('plm_standard', lmax, mmax)
+        with plan.lock:
+            std = plan.tables.get(skey)
+        if std is None:
+            std = _compat.plm_table(lmax, mmax, plan.costh)
+            with plan.lock:
+                plan.tables[skey] = std
+        given = arr[:lmax + 1, :mmax + 1, :]
+        if given.shape != std.shape:
+            raise ValueError('PLM must be at least (LMAX+1, MMAX+1, nlat); got %s' % (arr.shape,))
+        scale = max(float(np.abs(std).max()), 1.0)
+        diff = np.abs(given - std)
+        # NaNs in the caller's table count as "different": the table is then used as given
+        use_table = not bool(np.all(diff <= 1e-12 * scale))
     table = None
     if use_table:
         host = np.ascontiguousarray(np.transpose(np.asarray(PLM, dtype=np.float64)[:lmax + 1, :mmax + 1, :],

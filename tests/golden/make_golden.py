@@ -4,7 +4,8 @@ Generates ``tests/golden/*.npz`` by running the UNMODIFIED reference hot-path fi
 ``/root/reference`` (through ``oracle/ref_loader.py``) on seeded synthetic inputs.
 
 Run in the build container only (the reference tree does not travel):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                 # the small cases
+    python tests/golden/make_golden.py --big [names]   # BASELINE-size cases C2/C3/C4/C5 (minutes each)
 Each fixture stores the case parameters, a SHA-256 of the regenerated inputs, and the
 reference's clm/slm.  Inputs are not stored: ``tests/golden_cases.py`` rebuilds them from
 the same seeds.
@@ -22,11 +23,12 @@ from oracle import ref_loader          # noqa: E402
 import golden_cases                    # noqa: E402
 
 
-def main():
+def main(names=None, table=None):
     ref = ref_loader.load()
     outdir = os.path.dirname(os.path.abspath(__file__))
-    for name in golden_cases.CASES:
-        func, args, kwargs = golden_cases.build(name)
+    table = golden_cases.CASES if table is None else table
+    for name in (names or table):
+        func, args, kwargs = table[name]()
         Y = getattr(ref, func)(*args, **kwargs)
         path = os.path.join(outdir, name + '.npz')
         np.savez_compressed(path, clm=Y.clm, slm=Y.slm, lmax=int(Y.lmax), mmax=int(Y.mmax),
@@ -45,5 +47,9 @@ def hypsometric():
 
 
 if __name__ == '__main__':
-    main()
-    hypsometric()
+    if len(sys.argv) > 1 and sys.argv[1] == '--big':
+        # BASELINE-size cases (minutes of CPU each): all of them, or the ones named after --big
+        main(sys.argv[2:] or None, golden_cases.BIG_CASES)
+    else:
+        main()
+        hypsometric()
