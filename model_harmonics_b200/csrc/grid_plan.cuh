@@ -39,6 +39,11 @@ int moment_band_launch(mhb200_plan* pl, int nbands, int mode, int dtype, const v
                        double rad_e, int h0, int h1, int* slot_base, void* mom_ws, cudaStream_t st);
 int moment_band_finish(mhb200_plan* pl, int nbands, int mode, int nslots, const double* dfactor, double* clm,
                        double* slm, void* mom_ws, cudaStream_t st);
+bool moment_pressure_eligible(const mhb200_plan* pl, const double* plm_table);
+int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3], const double* G,
+                        const long long Gs[3], const double* R, const long long Rs[3], int nbatch, double rad_e,
+                        const double* dfactor, const double* dfactor_dev, double* clm, double* slm, void* mom_ws,
+                        const int** flag_out, cudaStream_t st);
 int moment_schedule(int nb, int nrings, int nchunks, int max_ctas, std::vector<int>& cta_unit,
                     std::vector<int>& cta_slot, std::vector<int>& field_slot, int* nslots);
 }  // namespace mhb

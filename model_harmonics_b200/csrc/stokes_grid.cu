@@ -1832,8 +1832,23 @@ int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const in
     gp.Rs[i] = Rs[i];
   }
   gp.rad_e = rad_e;
+  // Contracted-moment path (stokes_moments.cu); the direct kernels below then only run if it flagged a radius
+  // outside its validated range (|R / (rad_e r0(h)) - 1| <= 0.8 / (LMAX + 2) around every ring's mid-range).
+  if (moment_pressure_eligible(pl, plm_table)) {
+    const double* df_dev = nullptr;
+    if (pl->lmax + 1 > DF_MAX) {
+      if ((rc = ensure_stage(pl, (size_t)pl->lmax + 1)) != MHB200_OK) return rc;
+      if ((rc = stage(pl, dfactor, (size_t)pl->lmax + 1, 0, st)) != MHB200_OK) return rc;
+      df_dev = pl->stage_dev;
+    }
+    const int* flag = nullptr;
+    rc = moment_pressure_run(pl, P, gp.Ps, G, gp.Gs, R, gp.Rs, nbatch, rad_e, dfactor, df_dev, clm_out, slm_out,
+                             (char*)workspace + slots_bytes(pl, nbatch), &flag, st);
+    if (rc != MHB200_OK) return rc;
+    gp.run_flag = flag;
+  }
   if ((rc = launch_ring<MODE_PRESSURE, double>(gp, v, st)) != MHB200_OK) return rc;
-  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st);
+  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st, gp.run_flag);
 }
 
 int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH, const void* dP,

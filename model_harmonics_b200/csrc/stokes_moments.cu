@@ -237,8 +237,15 @@ __global__ void __launch_bounds__(256, 2)
 atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmP,
                   const __grid_constant__ AtmMomParams p) {
   extern __shared__ __align__(1024) unsigned char smraw[];
-  constexpr int STAGE_ELEMS = 2 * 4 * MLG * MKCF;
+  // A TMA box must start at a 16-byte aligned global address (measured: bench_micro/tma_probe.cu raises
+  // "illegal instruction" otherwise), and the mirrored runs start at odd longitudes: the box is BOXA
+  // elements wider than the 64 columns and starts at the aligned longitude below the run's first column.
+  constexpr int BOXA = 16 / (int)sizeof(Tin);
+  constexpr int BOXW = MKCF + BOXA;
+  constexpr int BOX_ELEMS = ((MLG * BOXW * (int)sizeof(Tin) + 127) / 128) * 128 / (int)sizeof(Tin);   // 128-byte pitch
+  constexpr int STAGE_ELEMS = 2 * 4 * BOX_ELEMS;
   constexpr uint32_t STAGE_BYTES = STAGE_ELEMS * sizeof(Tin);
+  constexpr uint32_t TX_BYTES = 2 * 4 * MLG * BOXW * sizeof(Tin);
   Tin* stages = reinterpret_cast<Tin*>(smraw);
   double* Mf = reinterpret_cast<double*>(smraw + MSTAGES * STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(Mf + 4 * MF_V);
@@ -271,14 +278,15 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     const int t = u / units_per_field, rem = u - t * units_per_field;
     const int h = p.h0 + rem / nchunks, c = rem % nchunks;
     const int tf = (p.fields_in_map > 1) ? t : 0;
-    mbar_expect_tx(&full[s], STAGE_BYTES);
+    mbar_expect_tx(&full[s], TX_BYTES);
     Tin* dst = stages + (size_t)s * STAGE_ELEMS;
     const int* bs = p.box_start + c * 4;
 #pragma unroll
     for (int sb = 0; sb < 4; ++sb) {
       const int x0 = __ldg(bs + sb);
-      tma_load_4d(dst + sb * MLG * MKCF, &tmZ, &full[s], x0, h, g * MLG, tf);
-      tma_load_4d(dst + (4 + sb) * MLG * MKCF, &tmP, &full[s], x0, h, g * MLG, tf);
+      const int xa = x0 - (((x0 % BOXA) + BOXA) % BOXA);
+      tma_load_4d(dst + sb * BOX_ELEMS, &tmZ, &full[s], xa, h, g * MLG, tf);
+      tma_load_4d(dst + (4 + sb) * BOX_ELEMS, &tmP, &full[s], xa, h, g * MLG, tf);
     }
   };
   for (int n = 0; n < MSTAGES - 1; ++n) issue(n);
@@ -293,21 +301,24 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   int item = 0;
 
   // geoid of this thread's column, fetched one unit ahead
-  auto column_of = [&](int u, int& col, double& geo) {
+  auto column_of = [&](int u, int& col, double& geo, int& shift) {
     const int t = u / units_per_field, rem = u - t * units_per_field;
     const int h = p.h0 + rem / nchunks, c = rem % nchunks;
     col = __ldg(p.col_grid + c * MKC + tid);
     geo = (col >= 0 && p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + col * p.geo_s1) : 0.0;
+    const int x0 = __ldg(p.box_start + c * 4 + sub);
+    shift = ((x0 % BOXA) + BOXA) % BOXA;          // columns between the aligned box start and the run
   };
-  int col_next;
+  int col_next, shift_next;
   double geo_next;
-  column_of(u_begin, col_next, geo_next);
+  column_of(u_begin, col_next, geo_next, shift_next);
 
   for (int u = u_begin; u < u_end; ++u) {
     const int t = u / units_per_field, rem = u - t * units_per_field;
     const int h = p.h0 + rem / nchunks, c = rem % nchunks;
     const bool active = (col_next >= 0);
     const double geo = geo_next;
+    const int bpos = shift_next + pos;
     double sg = 1.0, sp = 1.0;
     if (p.field_scale != nullptr) {
       sg = __ldg(p.field_scale + 2 * (p.t0 + t));
@@ -349,14 +360,14 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       issue(item + MSTAGES - 1);
       const int s = item % MSTAGES;
       mbar_wait(&full[s], (item / MSTAGES) & 1);
-      const Tin* zs = stages + (size_t)s * STAGE_ELEMS + sub * MLG * MKCF + pos;
-      const Tin* ps = zs + 4 * MLG * MKCF;
+      const Tin* zs = stages + (size_t)s * STAGE_ELEMS + sub * BOX_ELEMS + bpos;
+      const Tin* ps = zs + 4 * BOX_ELEMS;
       const int nl = min(MLG, p.nlev - g * MLG);
       double z[MLG], dpv[MLG];
 #pragma unroll
       for (int k = 0; k < MLG; ++k) {
-        z[k] = (k < nl) ? (double)zs[k * MKCF] : 0.0;
-        dpv[k] = (k < nl) ? (double)ps[k * MKCF] : 0.0;
+        z[k] = (k < nl) ? (double)zs[k * BOXW] : 0.0;
+        dpv[k] = (k < nl) ? (double)ps[k * BOXW] : 0.0;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -385,7 +396,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       ac[i] = __ldg(Ablk + i * 512);
       as[i] = __ldg(Ablk + i * 512 + 32);
     }
-    if (u + 1 < u_end) column_of(u + 1, col_next, geo_next);
+    if (u + 1 < u_end) column_of(u + 1, col_next, geo_next, shift_next);
 
     // fold over the four symmetric columns (phi, -phi, pi - phi, pi + phi), held by the lanes sub = 0..3 of
     // this warp: lane sub = v ends up with fold variant v (0 even-order cosine, 1 even sine, 2 odd cosine,
@@ -446,6 +457,191 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
         p.slot_ring[slot] = h;
       }
       ++slot;
+    }
+  }
+  if (__syncthreads_or(viol) && tid == 0) atomicOr(p.flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_A, surface pressure (gen_pressure_stokes.py:200-201): any LMAX.
+// Unit = (field, group of PNR rings, order block): the moments M_j = (P/G) d^j, d = R / (rad_e r0(h)) - 1,
+// of a chunk of 32 contraction columns x PNR rings are folded and contracted against the trig rows of the
+// order block; one trig fragment feeds 2 * PNR tiles.  r0(h) is the mid-range of R / rad_e over ring h
+// (scanned by the CTA), so |d| is half the ring's radius spread (topography: ~6e-4).
+// ------------------------------------------------------------------------------------------------
+constexpr int PNR = 4;                    // rings per unit
+constexpr int PKCF = 32;                  // contraction columns per chunk
+constexpr int PF_V = 8 * MF_KS + 8;       // folded-moment buffer: doubles per fold variant
+constexpr int PF_RING = 4 * PF_V;         // ... per ring
+
+struct PressMomParams {
+  int nlat, nlon, nchunks, ngroups, nmb, nks_total, Frows;
+  const int* col_grid;         // [nchunks][128] grid column of thread column (warp % 4, lane), -1 = inactive
+  const double *P, *G, *R;
+  long long Ps[3], Gs[3], Rs[3];
+  const double* trig;          // A fragments [nmb][nks_total][16 row tiles][32 lanes]
+  double* F;                   // [slot = field * nlat + ring][Frows orders][cs][16 moments]
+  double* slot_r0;
+  int* slot_ring;
+  int* flag;
+  double rad_e, inv_rad;
+  unsigned dbound_hi;
+};
+
+__global__ void __launch_bounds__(256, 2) pressure_moment_kernel(const __grid_constant__ PressMomParams p) {
+  extern __shared__ double psm[];
+  double* Mf = psm;                              // [PNR][4 variants][PF_V]
+  double* red = Mf + PNR * PF_RING;              // [2][PNR][8 warps]
+  double* ringc = red + 2 * PNR * 8;             // [PNR] r0, [PNR] 1 / (rad_e r0)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mb = blockIdx.x % p.nmb, rg = blockIdx.x / p.nmb, t = blockIdx.y;
+  const int hbase = rg * PNR;
+
+  // ---- expansion point of every ring of the group: mid-range of R over the ring
+  {
+    const double* Rt = p.R + t * p.Rs[0];
+#pragma unroll
+    for (int rr = 0; rr < PNR; ++rr) {
+      const int h = min(hbase + rr, p.nlat - 1);
+      double lo = 1.0e300, hi = -1.0e300;
+      for (int col = tid; col < p.nlon; col += 256) {
+        const double v = __ldg(Rt + h * p.Rs[1] + col * p.Rs[2]);
+        // a NaN radius must not be lost in the comparisons: it poisons both bounds
+        lo = (v < lo || v != v) ? v : lo;
+        hi = (v > hi || v != v) ? v : hi;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = (lo2 < lo || lo2 != lo2) ? lo2 : lo;
+        hi = (hi2 > hi || hi2 != hi2) ? hi2 : hi;
+      }
+      if (lane == 0) {
+        red[rr * 8 + warp] = lo;
+        red[(PNR + rr) * 8 + warp] = hi;
+      }
+    }
+    __syncthreads();
+    if (tid < PNR) {
+      double lo = red[tid * 8], hi = red[(PNR + tid) * 8];
+      for (int w = 1; w < 8; ++w) {
+        const double lo2 = red[tid * 8 + w], hi2 = red[(PNR + tid) * 8 + w];
+        lo = (lo2 < lo || lo2 != lo2) ? lo2 : lo;
+        hi = (hi2 > hi || hi2 != hi2) ? hi2 : hi;
+      }
+      const double r0 = (0.5 * (lo + hi)) * p.inv_rad;
+      ringc[tid] = r0;
+      ringc[PNR + tid] = 1.0 / (p.rad_e * r0);
+    }
+    __syncthreads();
+  }
+
+  // produce-phase role: two passes over ring pairs; thread column (warp % 4, lane) of ring 2 pass + tid / 128
+  const int sub = lane >> 3, jj = (warp & 3) * 8 + (lane & 7), rhalf = tid >> 7;
+  // contraction role
+  const int par = warp >> 2, gi = warp & 3;
+  double facc[PNR][2][2][2];
+#pragma unroll
+  for (int i = 0; i < PNR * 8; ++i) (&facc[0][0][0][0])[i] = 0.0;
+  int viol = 0;
+
+  struct Cell {
+    double P, G, R;
+    bool ok;
+  };
+  auto load_cell = [&](int c, int pass) -> Cell {
+    Cell x;
+    x.P = 0.0;
+    x.G = 1.0;
+    x.R = 0.0;
+    const int h = hbase + 2 * pass + rhalf;
+    const int col = (c < p.nchunks) ? __ldg(p.col_grid + c * 128 + (tid & 127)) : -1;
+    x.ok = (col >= 0 && h < p.nlat);
+    if (x.ok) {
+      x.P = __ldg(p.P + t * p.Ps[0] + h * p.Ps[1] + col * p.Ps[2]);
+      x.G = __ldg(p.G + t * p.Gs[0] + h * p.Gs[1] + col * p.Gs[2]);
+      x.R = __ldg(p.R + t * p.Rs[0] + h * p.Rs[1] + col * p.Rs[2]);
+    }
+    return x;
+  };
+  Cell cell[2];
+  cell[0] = load_cell(0, 0);
+  cell[1] = load_cell(0, 1);
+
+  for (int c = 0; c < p.nchunks; ++c) {
+    // first trig fragments of the chunk
+    const double* Ablk = p.trig + (((size_t)mb * p.nks_total + c * 8) * 16 + (par * 4 + gi) * 2) * 32 + lane;
+    double ac[4], as[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ac[i] = __ldg(Ablk + i * 512);
+      as[i] = __ldg(Ablk + i * 512 + 32);
+    }
+    __syncthreads();          // previous chunk's contraction has read Mf
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int rr = 2 * pass + rhalf;
+      double f = 0.0, d = 0.0;
+      if (cell[pass].ok) {
+        f = cell[pass].P / cell[pass].G;                       // :200, true division
+        d = fma(cell[pass].R, ringc[PNR + rr], -1.0);
+        viol |= ((unsigned)(__double2hiint(d) & 0x7fffffff) > p.dbound_hi) ? 1 : 0;
+      }
+      double* dst = Mf + rr * PF_RING + sub * PF_V + (jj >> 2) * MF_KS + (jj & 3);
+      double mj = f;
+#pragma unroll
+      for (int j = 0; j < NMOMC; ++j) {
+        // fold over the four symmetric columns (see atm_moment_kernel)
+        double x = mj;
+        const double y = __shfl_xor_sync(0xffffffffu, x, 8);
+        x = (sub & 1) ? (y - x) : (x + y);
+        const double zz = __shfl_xor_sync(0xffffffffu, x, 16);
+        dst[(j >> 3) * 32 + (j & 7) * 4] = (sub == 1) ? (x - zz) : (sub == 2) ? (zz - x) : (x + zz);
+        mj *= d;
+      }
+    }
+    __syncthreads();
+    // next chunk's cells: their latency hides behind the contraction
+    cell[0] = load_cell(c + 1, 0);
+    cell[1] = load_cell(c + 1, 1);
+    {
+      const double* Bc = Mf + (2 * par) * PF_V + lane;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const double a_c = ac[ks & 3], a_s = as[ks & 3];
+        if (ks + 4 < 8) {
+          ac[ks & 3] = __ldg(Ablk + (ks + 4) * 512);
+          as[ks & 3] = __ldg(Ablk + (ks + 4) * 512 + 32);
+        }
+#pragma unroll
+        for (int rr = 0; rr < PNR; ++rr) {
+          const double* B = Bc + rr * PF_RING + ks * MF_KS;
+          const double b0 = B[0], b1 = B[32], b2 = B[PF_V], b3 = B[PF_V + 32];
+          dmma884(facc[rr][0][0][0], facc[rr][0][0][1], a_c, b0);
+          dmma884(facc[rr][0][1][0], facc[rr][0][1][1], a_c, b1);
+          dmma884(facc[rr][1][0][0], facc[rr][1][0][1], a_s, b2);
+          dmma884(facc[rr][1][1][0], facc[rr][1][1][1], a_s, b3);
+        }
+      }
+    }
+  }
+  // flush: one slot per (field, ring)
+  const int m = mb * MBLK + 16 * gi + 2 * (lane >> 2) + par;
+#pragma unroll
+  for (int rr = 0; rr < PNR; ++rr) {
+    const int h = hbase + rr;
+    if (h < p.nlat) {
+      const int slot = t * p.nlat + h;
+      double* Fs = p.F + ((size_t)slot * p.Frows + m) * 32 + 2 * (lane & 3);
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+          *reinterpret_cast<double2*>(Fs + cs * 16 + nt * 8) = make_double2(facc[rr][cs][nt][0], facc[rr][cs][nt][1]);
+      if (mb == 0 && tid == rr) {
+        p.slot_r0[slot] = ringc[rr];
+        p.slot_ring[slot] = h;
+      }
     }
   }
   if (__syncthreads_or(viol) && tid == 0) atomicOr(p.flag, 1);
@@ -627,6 +823,8 @@ struct MomentPlan {
   int nchunks = 0, nf = 0, nunits = 0, ncta_max = 0;
   int dir[4] = {1, 1, 1, 1};
   int *box_start = nullptr, *col_grid = nullptr, *unit_lm = nullptr, *lb_unit0 = nullptr;
+  int nchunks32 = 0;
+  int* col_grid32 = nullptr;            // pressure kernel: [nchunks32][128]
   double* trig = nullptr;               // [nmb][nchunks * 16][16][32]
   double* E = nullptr;                  // [2][16][lmax + 1]: n0 = 2, n0 = 4
   std::vector<MomSchedule> sched;
@@ -662,6 +860,12 @@ MomWs mom_layout(const mhb200_plan* pl, size_t max_slots, size_t g_units) {
   o = align256(o + g_units * G_UNIT * sizeof(double));
   w.total = o;
   return w;
+}
+
+// fields per K_A launch: at most NB_SUB, fewer when a slot is large (LMAX 360: 98 KB per ring)
+int nb_sub(const mhb200_plan* pl) {
+  const double per_field = (double)pl->nlat * pl->Mpad * 32.0 * sizeof(double);
+  return std::max(1, std::min(NB_SUB, (int)(256.0e6 / per_field)));
 }
 
 int pick_nsplit(const mhb200_plan* pl, int nb) {
@@ -703,7 +907,7 @@ int make_cube_map(CUtensorMap* tm, const void* base, int dtype, int nlon, int nl
   cuuint64_t dims[4] = {(cuuint64_t)nlon, (cuuint64_t)nlat, (cuuint64_t)nlev, (cuuint64_t)std::max(nfields, 1)};
   cuuint64_t strides[3] = {(cuuint64_t)nlon * esz, (cuuint64_t)nlon * nlat * esz,
                            (cuuint64_t)(nfields > 1 ? batch_stride : (long long)nlon * nlat * nlev) * esz};
-  cuuint32_t box[4] = {(cuuint32_t)MKCF, 1, (cuuint32_t)MLG, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(MKCF + 16 / esz), 1, (cuuint32_t)MLG, 1};   // see atm_moment_kernel (BOXW)
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(tm, dtype == MHB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -821,6 +1025,13 @@ int moment_plan_create(mhb200_plan* pl, const double* phi) {
       box_start[(size_t)c * 4 + sb] = have ? start : 0;
     }
   mp->tma_ok = ok;
+  // pressure kernel: chunks of 32 contraction columns, thread column (warp % 4, lane)
+  mp->nchunks32 = (nf + PKCF - 1) / PKCF;
+  std::vector<int> col_grid32((size_t)mp->nchunks32 * 128, -1);
+  for (int c = 0; c < mp->nchunks32; ++c)
+    for (int sb = 0; sb < 4; ++sb)
+      for (int jj = 0; jj < PKCF; ++jj)
+        col_grid32[(size_t)c * 128 + (jj >> 3) * 32 + sb * 8 + (jj & 7)] = column(sb, c * PKCF + jj);
   // trig table (m_phi of gen_pressure_stokes.py:176-177 on the contraction columns), fragment-major:
   // row tile (par*4 + gi)*2 + {cos, sin}, row r: order 64 mb + 16 gi + 2 r + par; k: column 4 ks + lane % 4
   const int nks = mp->nchunks * 16;
@@ -862,6 +1073,7 @@ int moment_plan_create(mhb200_plan* pl, const double* phi) {
     }
   int rc;
   if ((rc = upload_vec(&mp->col_grid, col_grid)) || (rc = upload_vec(&mp->box_start, box_start)) ||
+      (rc = upload_vec(&mp->col_grid32, col_grid32)) ||
       (rc = upload_vec(&mp->trig, trig)) || (rc = upload_vec(&mp->unit_lm, unit_lm)) ||
       (rc = upload_vec(&mp->lb_unit0, lb_unit0)) || (rc = upload_vec(&mp->E, E)))
     return rc;
@@ -873,6 +1085,7 @@ void moment_plan_destroy(mhb200_plan* pl) {
   if (!mp) return;
   cudaFree(mp->box_start);
   cudaFree(mp->col_grid);
+  cudaFree(mp->col_grid32);
   cudaFree(mp->unit_lm);
   cudaFree(mp->lb_unit0);
   cudaFree(mp->trig);
@@ -888,7 +1101,7 @@ void moment_plan_destroy(mhb200_plan* pl) {
 // bytes of the moment region for calls with up to nb_max fields per launch and `launches` K_A launches
 size_t moment_workspace_bytes(const mhb200_plan* pl, int nbatch, int launches) {
   if (!pl->mom) return 0;
-  const int nb = std::min(nbatch, NB_SUB);
+  const int nb = std::min(nbatch, nb_sub(pl));
   const size_t max_slots = (size_t)nb * pl->nlat + (size_t)launches * pl->mom->ncta_max;
   return mom_layout(pl, max_slots, g_units_bound(pl, nb)).total;
 }
@@ -926,7 +1139,8 @@ struct MomCall {
 static int launch_atm_kernel(const MomCall& c, const CUtensorMap& tz, const CUtensorMap& tp, const AtmMomParams& ap,
                              int ncta, cudaStream_t st) {
   const size_t esz = (c.dtype == MHB200_F64) ? 8 : 4;
-  const size_t smem = (size_t)MSTAGES * 2 * 4 * MLG * MKCF * esz + 4 * MF_V * sizeof(double) + 2 * MSTAGES * 8;
+  const size_t box_bytes = ((MLG * (MKCF + 16 / esz) * esz + 127) / 128) * 128;
+  const size_t smem = (size_t)MSTAGES * 2 * 4 * box_bytes + 4 * MF_V * sizeof(double) + 2 * MSTAGES * 8;
 #define MHB_LAUNCH_ATM(MODE, T)                                                                              \
   do {                                                                                                       \
     auto kern = atm_moment_kernel<MODE, T>;                                                                  \
@@ -1062,7 +1276,7 @@ int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const 
                    const double* field_scale_dev, const double* geoid, long long geo_s0, long long geo_s1,
                    const double* ring_tab, int nlev, int nbatch, double rad_e, const double* dfactor,
                    double* clm, double* slm, void* mom_ws, const int** flag_out, cudaStream_t st) {
-  const int nbmax = std::min(nbatch, NB_SUB);
+  const int nbmax = std::min(nbatch, nb_sub(pl));
   const MomWs lay = mom_layout(pl, (size_t)nbmax * pl->nlat + pl->mom->ncta_max, g_units_bound(pl, nbmax));
   char* ws = (char*)mom_ws;
   MHB_CUDA(cudaMemsetAsync(ws + lay.flag, 0, sizeof(int), st));
@@ -1082,8 +1296,8 @@ int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const 
   c.rad_e = rad_e;
   const size_t nout = (size_t)(pl->lmax + 1) * (pl->mmax + 1);
   const int noff = (mode == MHB200_METHOD_BC05) ? 2 : 4;
-  for (int t0 = 0; t0 < nbatch; t0 += NB_SUB) {
-    const int nb = std::min(NB_SUB, nbatch - t0);
+  for (int t0 = 0; t0 < nbatch; t0 += nbmax) {
+    const int nb = std::min(nbmax, nbatch - t0);
     MomSchedule* sc = nullptr;
     int rc = moment_atm_launch(pl, c, lay, ws, t0, nb, 0, pl->nlat, 0, &sc, st);
     if (rc != MHB200_OK) return rc;
@@ -1134,4 +1348,86 @@ int moment_band_finish(mhb200_plan* pl, int nbands, int mode, int nslots, const 
                        clm, slm, st);
 }
 
+bool moment_pressure_eligible(const mhb200_plan* pl, const double* plm_table) {
+  return pl->mom != nullptr && plm_table == nullptr && moment_mode_env() >= 2;
+}
+
+// gen_pressure_stokes through K_A (pressure), K_B, K_C; sub-batches of nb_sub(pl) fields
+int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3], const double* G,
+                        const long long Gs[3], const double* R, const long long Rs[3], int nbatch, double rad_e,
+                        const double* dfactor, const double* dfactor_dev, double* clm, double* slm, void* mom_ws,
+                        const int** flag_out, cudaStream_t st) {
+  MomentPlan* mp = pl->mom;
+  const int nbmax = std::min(nbatch, nb_sub(pl));
+  const MomWs lay = mom_layout(pl, (size_t)nbmax * pl->nlat + mp->ncta_max, g_units_bound(pl, nbmax));
+  char* ws = (char*)mom_ws;
+  MHB_CUDA(cudaMemsetAsync(ws + lay.flag, 0, sizeof(int), st));
+  *flag_out = (const int*)(ws + lay.flag);
+  const size_t nout = (size_t)(pl->lmax + 1) * (pl->mmax + 1);
+  const size_t smem = (size_t)(PNR * PF_RING + 2 * PNR * 8 + 2 * PNR) * sizeof(double);
+  MHB_CUDA(cudaFuncSetAttribute(pressure_moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int t0 = 0; t0 < nbatch; t0 += nbmax) {
+    const int nb = std::min(nbmax, nbatch - t0);
+    PressMomParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.nlat = pl->nlat;
+    pp.nlon = pl->nlon;
+    pp.nchunks = mp->nchunks32;
+    pp.ngroups = (pl->nlat + PNR - 1) / PNR;
+    pp.nmb = pl->nmb;
+    pp.nks_total = mp->nchunks * 16;
+    pp.Frows = pl->Mpad;
+    pp.col_grid = mp->col_grid32;
+    pp.P = P + (size_t)t0 * Ps[0];
+    pp.G = G + (size_t)t0 * Gs[0];
+    pp.R = R + (size_t)t0 * Rs[0];
+    for (int i = 0; i < 3; ++i) {
+      pp.Ps[i] = Ps[i];
+      pp.Gs[i] = Gs[i];
+      pp.Rs[i] = Rs[i];
+    }
+    pp.trig = mp->trig;
+    pp.F = (double*)(ws + lay.F);
+    pp.slot_r0 = (double*)(ws + lay.slot_r0);
+    pp.slot_ring = (int*)(ws + lay.slot_ring);
+    pp.flag = (int*)(ws + lay.flag);
+    pp.rad_e = rad_e;
+    pp.inv_rad = 1.0 / rad_e;
+    const double bound = MOM_ND_BOUND / (double)(pl->lmax + 2);
+    unsigned long long bits;
+    memcpy(&bits, &bound, 8);
+    pp.dbound_hi = (unsigned)(bits >> 32);
+    profile_begin(st);
+    pressure_moment_kernel<<<dim3(pp.ngroups * pp.nmb, nb), 256, smem, st>>>(pp);
+    profile_end(st);
+    g_launches.fetch_add(1);
+    MHB_CUDA(cudaGetLastError());
+    int field_slot[NB_SUB + 1];
+    for (int i = 0; i <= nb; ++i) field_slot[i] = i * pl->nlat;
+    const int rc = moment_reduce(pl, lay, ws, nb, field_slot, 2, dfactor, dfactor_dev, clm + t0 * nout,
+                                 slm + t0 * nout, st);
+    if (rc != MHB200_OK) return rc;
+  }
+  return MHB200_OK;
+}
+
 }  // namespace mhb
+
+extern "C" {
+// CPU-testable probe of the moment path's static schedule (no CUDA calls): fills cta_unit[ncta + 1],
+// cta_slot[ncta], field_slot[nb + 1]; returns the number of CTAs (or -1), *nslots_out = slots.
+int mhb200_moment_schedule_probe(int nb, int nrings, int nchunks, int max_ctas, int* cta_unit, int* cta_slot,
+                                 int* field_slot, int buf_ctas, int* nslots_out) {
+  if (nb < 1 || nrings < 1 || nchunks < 1 || max_ctas < 1 || !cta_unit || !cta_slot || !field_slot || !nslots_out)
+    return -1;
+  std::vector<int> cu, cs, fs;
+  int nslots = 0;
+  const int ncta = mhb::moment_schedule(nb, nrings, nchunks, max_ctas, cu, cs, fs, &nslots);
+  if (ncta + 1 > buf_ctas) return -1;
+  for (int i = 0; i <= ncta; ++i) cta_unit[i] = cu[i];
+  for (int i = 0; i < ncta; ++i) cta_slot[i] = cs[i];
+  for (int i = 0; i <= nb; ++i) field_slot[i] = fs[i];
+  *nslots_out = nslots;
+  return ncta;
+}
+}
