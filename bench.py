@@ -13,14 +13,20 @@ on load from one device-resident base cube by the IEEE-exact scalings of SURVEY.
 (GPH_t = GPH_0 (1+a_t), dP_t = dP_0 (1+b_t)); with N > 1 every rank takes its own time steps
 (weak scaling) and the step ends with the NCCL gather of the coefficient blocks.
 
-value   : whole-job fields/s with inputs resident in HBM (CUDA events, max over ranks).
+value   : whole-job fields/s with inputs resident in HBM (CUDA events, max over ranks); the --fields
+          fields of a step are DISTINCT cubes (8 x 615 MB), so every byte comes from DRAM.
 e2e     : the same metric through the drop-in Python call gen_atmosphere_stokes with HOST
           (pinned) fp64 cubes: H2D of both cubes and D2H of the coefficients inside the timed
           region, every field.
-roofline: algorithmic fp64 flops of SURVEY.md 8(d) per launch / device time of
-          stokes_ring_kernel (CUDA events on its own stream, inside the timed region) against
-          the measured fp64 DMMA peak (profiles/r01_fp64_peaks.jsonl; MEASURED_PEAKS.json has
-          no fp64 figure), plus the HBM view of the same launch.
+roofline: algorithmic bytes of SURVEY.md 8(d) per launch / device time of atm_moment_kernel (CUDA
+          events on its own stream, inside the timed region) against the measured HBM peak
+          (MEASURED_PEAKS.json) -- the floor of this workload now that the contracted-moment form
+          has cut the fp64 work ~5x; the fp64 views (direct-sum flop model, executed-flop model,
+          ncu pipe utilisation) sit beside it under roofline.fp64.  traffic = DRAM bytes of the
+          same batched launch measured under ncu (profiles/r02_atm_moment_batch8.json).
+c5_480_field_job: BASELINE.json configs[4] -- 480 fields time-sharded over the ranks (strong
+          scaling), one gather at the end, wall clock barrier -> gather, parity of
+          t in {0, 7, 123, 479} against reference-generated goldens.
 cpu_baseline / --impl reference: the NumPy oracle port of the reference's algorithm on the
           box's host cores, process-parallel over time steps, on a bounded latitude sample.
 """
@@ -46,6 +52,12 @@ def algorithmic_flops_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON, L=LMAX):
     ntri = (L + 1) * (L + 2) // 2
     f_grid = nlat * nlon * (4 * ntri + (L + 1) + 1) + nlat * ntri * 8
     return nlev * nlat * nlon * (3 * (L + 1) + 50) + f_grid
+
+
+def executed_flops_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON):
+    """fp64 operations atm_moment_kernel issues per field: per (level, column) element
+    23 slots of geometry + 23 of moment accumulation, per column 512 FMA-slots of DMMA contraction."""
+    return 2 * nlat * nlon * (nlev * 46 + 512)
 
 
 def algorithmic_bytes_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON, itemsize=8):
@@ -125,7 +137,9 @@ def run_reference_arm(args):
 def workload_config(args, cores=None):
     return {'workload': 'atmosphere_c3', 'operator': 'gen_atmosphere_stokes', 'method': 'BC05',
             'grid': '%dx%dx%d' % (NLEV, NLAT, NLON), 'lmax': LMAX, 'fields_per_step_per_gpu': args.fields,
-            'input_dtype': 'f64', 'l2_policy': 'inputs exceed L2 (615 MB per field vs 126 MB)',
+            'input_dtype': 'f64',
+            'l2_policy': 'inputs exceed L2: %d distinct device-resident cubes per step, 615 MB each, vs 126 MB of L2'
+                         % args.fields,
             'parallelism': 'time-sharded x%d' % args.gpus}
 
 
@@ -204,6 +218,50 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local):
+    """
+    Pins this process (and therefore the first-touch placement of its pinned host buffers) to the CPUs of
+    the NUMA node its GPU hangs off, so that N ranks do not all stream from node 0.  Returns a description.
+    """
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        if node < 0:
+            return {'numa_node': None, 'note': 'no NUMA affinity reported for %s' % bus}
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {'numa_node': node, 'cpus': len(cpus)}
+    except Exception as exc:      # containers often hide sysfs: report, do not fail
+        return {'numa_node': None, 'note': '%s: %s' % (type(exc).__name__, exc)}
+
+
+def load_profile_record(name):
+    """Figures measured under ncu on the same launch shape and committed under profiles/ (or None)."""
+    path = os.path.join(ROOT, 'profiles', name)
+    if os.path.isfile(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+def golden_error(np, clm, slm, name):
+    """max|delta| / max|ref| against a committed reference-generated golden (tests/golden/<name>.npz)."""
+    path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+    if not os.path.isfile(path):
+        return None
+    gold = np.load(path)
+    scale = max(np.abs(gold['clm']).max(), np.abs(gold['slm']).max())
+    return float(max(np.abs(clm - gold['clm']).max(), np.abs(slm - gold['slm']).max()) / scale)
+
+
 def run_cuda_arm(args):
     import numpy as np
     import torch
@@ -217,10 +275,11 @@ def run_cuda_arm(args):
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         import datetime
         dist.init_process_group('nccl', device_id=torch.device('cuda', local),
-                                timeout=datetime.timedelta(seconds=120))
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local)
     L = _lib.lib()
     T = args.fields
@@ -230,11 +289,16 @@ def run_cuda_arm(args):
     LOVE = syn.love_numbers(LMAX)
     g, d, ge = torch.from_numpy(GPH).to(dev), torch.from_numpy(dP).to(dev), torch.from_numpy(geoid).to(dev)
     kw = dict(LMAX=LMAX, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE, METHOD='BC05')
-    # this rank's time steps (global index = rank*T + i), SURVEY.md 8(d) scalings
+    # this rank's time steps (global index = rank*T + i), SURVEY.md 8(d): GPH_t = GPH_0 (1 + a_t),
+    # dP_t = dP_0 (1 + b_t), IEEE-exact elementwise products -- T DISTINCT device-resident cubes
+    # (T x 615 MB), so every field of a step is read from DRAM, not from L2
     scales = np.array([syn.atmosphere_field_scalars(rank * T + i) for i in range(T)])
+    sc = torch.from_numpy(scales).to(dev)
+    g8 = (g[None] * sc[:, 0, None, None, None]).contiguous()
+    d8 = (d[None] * sc[:, 1, None, None, None]).contiguous()
 
     def step():
-        clm, slm = mh.atmosphere_stokes_batch(g, d, lon, lat, field_scale=scales, as_numpy=False, **kw)
+        clm, slm = mh.atmosphere_stokes_batch(g8, d8, lon, lat, as_numpy=False, **kw)
         blk = torch.stack([clm, slm], dim=1)
         if world > 1:
             blk = batch.gather_coefficients(blk, world * T)      # the only collective: final gather
@@ -280,6 +344,40 @@ def run_cuda_arm(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     value = world * T * args.steps / (ms * 1e-3)
+    # parity of what was timed, against committed reference-generated goldens (rank 0 holds t = 0 and 7)
+    spot = {}
+    if rank == 0:
+        res = out.cpu().numpy()
+        for t in (0, 7):
+            if t < T:
+                spot['t%d' % t] = golden_error(np, res[t, 0], res[t, 1], 'atmosphere_c5_t%d' % t)
+    del g8, d8
+
+    # ---- the 480-field job (BASELINE.json configs[4]): strong scaling, fields derived on load from the
+    #      resident base cube, one plan, ONE gather at the end; wall time barrier -> gather
+    c5 = None
+    if not args.no_c5:
+        NF = args.c5_fields
+        c5_scales = np.array([syn.atmosphere_field_scalars(t) for t in range(NF)])
+        kw5 = dict(LMAX=LMAX, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE, METHOD='BC05')
+        batch.atmosphere_stokes_sharded(g, d, lon, lat, c5_scales[:world * 8], **kw5)       # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        c5_clm, c5_slm = batch.atmosphere_stokes_sharded(g, d, lon, lat, c5_scales, **kw5)
+        barrier()
+        c5_s = time.perf_counter() - t0
+        if world > 1:
+            ts = torch.tensor([c5_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            c5_s = float(ts.item())
+        if rank == 0:
+            cc, ss = c5_clm.cpu().numpy(), c5_slm.cpu().numpy()
+            c5 = {'fields': NF, 'scaling': 'strong', 'seconds': c5_s, 'fields_per_s': NF / c5_s,
+                  'fields_per_rank': [batch.shard_range(NF, r, world)[1] - batch.shard_range(NF, r, world)[0]
+                                      for r in range(world)],
+                  'collective': 'one all_gather_into_tensor of (T, 2, 61, 61) fp64 at the end' if world > 1 else None,
+                  'parity_vs_reference_golden': {('t%d' % t): golden_error(np, cc[t], ss[t], 'atmosphere_c5_t%d' % t)
+                                                 for t in (0, 7, 123, 479) if t < NF}}
 
     # ---- end to end through the drop-in call with pinned host cubes (H2D + D2H every field)
     nf = 2
@@ -309,6 +407,8 @@ def run_cuda_arm(args):
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         e2e_s = float(ts.item())
     e2e_value = world * nf * e2e_steps / e2e_s
+    if rank == 0:
+        spot['e2e_t0'] = golden_error(np, Y[0].clm, Y[0].slm, 'atmosphere_c5_t0')
     # same call with the cubes in their on-disk storage type (float32, widened exactly on the device)
     host32 = []
     for hg, hd in host[:1]:
@@ -332,30 +432,24 @@ def run_cuda_arm(args):
     h2d = nf * algorithmic_bytes_per_field()
     d2h = nf * 2 * (LMAX + 1) * (LMAX + 1) * 8
 
-    # parity spot check of what was timed (device-resident field 0 of this rank vs the e2e result)
-    chk = float((out[rank * T if world > 1 else 0, 0].cpu() - torch.from_numpy(Y[0].clm)).abs().max() /
-                np.abs(Y[0].clm).max())
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    flops = algorithmic_flops_per_field() * T
-    achieved = flops / (ring_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'ring_kernel_traffic.json')
-    if os.path.isfile(tpath):
-        try:
-            traffic = int(json.load(open(tpath))['dram_bytes_per_field'] * T)
-        except Exception:
-            traffic = None
     peaks = {}
     ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(ppath):
         peaks = json.load(open(ppath))
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
-    hbm_achieved = algorithmic_bytes_per_field() * T / (ring_ms * 1e-3) / 1e9
+    # dominant kernel = atm_moment_kernel (K_A of the contracted-moment path): one launch per step
+    alg_bytes = algorithmic_bytes_per_field() * T
+    hbm_achieved = alg_bytes / (ring_ms * 1e-3) / 1e9
+    flops = algorithmic_flops_per_field() * T
+    prof = load_profile_record('r02_atm_moment_batch8.json') or {}
+    traffic = None
+    if prof.get('fields_per_launch') == T:
+        traffic = int(prof['dram_bytes_read'] + prof['dram_bytes_write'])
 
     line = {
         'metric': 'fields_to_stokes_per_second', 'value': value, 'unit': 'fields/s', 'n_gpus': world,
@@ -364,26 +458,51 @@ def run_cuda_arm(args):
         'config': workload_config(args),
         'e2e': {'value': e2e_value, 'unit': 'fields/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'fields_per_step': nf, 'steps': e2e_steps, 'call': 'gen_atmosphere_stokes(pinned NumPy fp64 cubes)',
-                'pipeline': '8 latitude bands: H2D of band b+1 overlaps the kernel of band b',
+                'pipeline': '8 latitude bands: H2D of band b+1 overlaps the kernels of band b',
+                'h2d_gb_per_s_aggregate': e2e_value * algorithmic_bytes_per_field() / 1e9,
+                'numa': numa,
                 'float32_stored_cubes': {'value': e2e32_value, 'unit': 'fields/s',
-                                         'h2d_bytes_per_field': algorithmic_bytes_per_field(itemsize=4)}},
+                                         'h2d_bytes_per_field': algorithmic_bytes_per_field(itemsize=4),
+                                         'h2d_gb_per_s_aggregate':
+                                             e2e32_value * algorithmic_bytes_per_field(itemsize=4) / 1e9}},
         'gpu_launches': launches,
-        'roofline': {'bound': 'tensor', 'kernel': 'stokes_ring_kernel', 'achieved': achieved,
-                     'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS,
-                     'traffic': traffic, 'kernel_ms': ring_ms, 'launches_timed': int(nrec.value),
-                     'flops_per_launch': flops,
-                     'peak_source': 'fp64 DMMA m8n8k4 peak measured on this pool (profiles/r01_fp64_peaks.jsonl); '
-                                    'MEASURED_PEAKS.json holds no fp64 figure; DFMA and DMMA share one pipe',
-                     'hbm': {'achieved': hbm_achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                             'frac': hbm_achieved / hbm_peak,
-                             'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
+        # The contracted-moment form executes ~5x fewer fp64 operations than the direct sum SURVEY 8(d)
+        # counts, so the floor of this workload is the HBM stream (614.6 MB per field, 94 us at the measured
+        # peak): the roofline is quoted against HBM, with the fp64 views beside it.
+        'roofline': {'bound': 'hbm', 'kernel': 'atm_moment_kernel', 'achieved': hbm_achieved, 'peak': hbm_peak,
+                     'unit': 'GB/s', 'frac': hbm_achieved / hbm_peak, 'traffic': traffic,
+                     'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': ring_ms,
+                     'launches_timed': int(nrec.value),
+                     'peak_source': 'MEASURED_PEAKS.json (burst copy bandwidth)' if peaks else 'fallback',
+                     'traffic_source': 'profiles/r02_atm_moment_batch8.json: dram__bytes_read.sum + '
+                                       'dram__bytes_write.sum of the same batched launch under ncu --set full'
+                                       if traffic else None,
+                     'fp64': {
+                         'direct_sum_model': {
+                             'flops_per_launch': flops, 'achieved_tflops': flops / (ring_ms * 1e-3) / 1e12,
+                             'peak_tflops': FP64_PEAK_TFLOPS,
+                             'frac': flops / (ring_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                             'note': 'SURVEY 8(d) flop count of the reference formulation; the moment form '
+                                     'removes most of these operations, so this can exceed 1'},
+                         'executed_model': {
+                             'flops_per_launch': executed_flops_per_field() * T,
+                             'achieved_tflops': executed_flops_per_field() * T / (ring_ms * 1e-3) / 1e12,
+                             'frac': executed_flops_per_field() * T / (ring_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                             'note': 'fp64 operations the kernel issues (46 FMA-slots per level element + 512 per '
+                                     'column in the DMMA contraction, FMA = 2 flops)'},
+                         'pipe_busy_pct_ncu': prof.get('pipe_fp64_plus_dmma_pct'),
+                         'peak_source': 'fp64 DMMA m8n8k4 peak measured on this pool '
+                                        '(profiles/r01_fp64_peaks.jsonl); DFMA and DMMA share one pipe'}},
         'clocks': clocks,
-        'parity_spot_check_rel_to_max': chk,
+        'parity_vs_reference_golden': spot,
     }
+    if c5 is not None:
+        line['c5_480_field_job'] = c5
     if world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp
         cores = os.cpu_count() or 1
         with mp.get_context('spawn').Pool(cores) as pool:
+            cpu_arm_step(pool, cores)                  # untimed warm-up (imports, page cache), as in the reference arm
             cpu_value, wall = cpu_arm_step(pool, cores)
         line['cpu_baseline'] = {'value': cpu_value, 'unit': 'fields/s', 'cores': cores, 'kind': 'port',
                                 'sample': cpu_sample_description(), 'seconds': wall}
@@ -489,6 +608,8 @@ def main():
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true')
+    ap.add_argument('--no-c5', action='store_true', help='skip the 480-field strong-scaling job')
+    ap.add_argument('--c5-fields', type=int, default=480)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -11,6 +11,16 @@ if case == 'c3':
     GPH, dP, geoid = syn.atmosphere_cube(37, 721, 1440)
     g, d, ge = torch.from_numpy(GPH).cuda(), torch.from_numpy(dP).cuda(), torch.from_numpy(geoid).cuda()
     f = lambda: mh.atmosphere_stokes_batch(g[None], d[None], lon, lat, as_numpy=False, LMAX=60, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE)
+elif case == 'c3b':
+    # batch of 8 DISTINCT cubes (8 x 615 MB)
+    lon, lat = syn.grid_axes(721, 1440)
+    GPH, dP, geoid = syn.atmosphere_cube(37, 721, 1440)
+    sc = np.array([syn.atmosphere_field_scalars(t) for t in range(8)])
+    g = torch.from_numpy(GPH).cuda(); d = torch.from_numpy(dP).cuda(); ge = torch.from_numpy(geoid).cuda()
+    g8 = (g[None] * torch.from_numpy(sc[:, 0]).cuda()[:, None, None, None]).contiguous()
+    d8 = (d[None] * torch.from_numpy(sc[:, 1]).cuda()[:, None, None, None]).contiguous()
+    del g, d
+    f = lambda: mh.atmosphere_stokes_batch(g8, d8, lon, lat, as_numpy=False, LMAX=60, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE)
 elif case == 'c1':
     lon, lat = syn.grid_axes(181, 360); G, R = syn.surface_geometry(lon, lat); P = syn.pressure_fields(181, 360, 12)
     Pd, Gd, Rd = [torch.from_numpy(a).cuda() for a in (P, G, R)]

@@ -22,6 +22,15 @@
  *   - return value: MHB200_OK or a negative MHB200_E* code;
  *     mhb200_last_error() gives a thread-local message.
  *   - there is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Kernel paths of the grid operators (same results to rounding)
+ *   - contracted-moment path (default; csrc/stokes_moments.cu): regular longitude grids with both
+ *     mirror symmetries, no caller-supplied PLM table; the atmosphere form also needs LMAX <= 63 and
+ *     16-byte aligned cubes / rows (TMA).  It is guarded: every call also enqueues the direct kernels,
+ *     which exit at once unless a radius left the validated range of the binomial expansion
+ *     (|r / r0 - 1| <= 0.8 / (LMAX + 2 or 4)), in which case they recompute the call exactly.
+ *   - direct kernels (csrc/stokes_grid.cu): any grid, any LMAX, caller PLM tables.
+ *   MHB200_MOMENTS=0 forces the direct kernels, =1 the round-1 expanded-moment variant (unguarded).
  */
 #ifndef MHB200_H_
 #define MHB200_H_
@@ -182,6 +191,15 @@ int mhb200_schedule_probe(int nlat, int nchunks, int nlb, int nmb, int nbatch, i
                           int* cta_begin, int max_ctas_buf, int* ncta_out);
 int mhb200_fold_probe(int nlon, const double* phi, int nth, int* sets, int* unused, int* fold_out,
                       int* nchunks_out, int* kcf_out);
+
+/*
+ * mhb200_moment_schedule_probe: static schedule of the contracted-moment atmosphere kernel
+ *   (csrc/stokes_moments.cu): the nb * nrings * nchunks (field, ring, 64-column chunk) units are split
+ *   evenly over at most max_ctas CTAs; a slot is the part of one ring a CTA owns.  Fills
+ *   cta_unit[ncta + 1], cta_slot[ncta], field_slot[nb + 1]; returns ncta (or -1), *nslots_out = slots.
+ */
+int mhb200_moment_schedule_probe(int nb, int nrings, int nchunks, int max_ctas, int* cta_unit,
+                                 int* cta_slot, int* field_slot, int buf_ctas, int* nslots_out);
 
 /* counters for bench.py: kernels launched by this library since load (all threads) */
 uint64_t mhb200_launch_count(void);

@@ -1,0 +1,167 @@
+"""
+GPU tests of the contracted-moment kernels (csrc/stokes_moments.cu) and of their guard: the binomial
+expansion is valid for |r / r0 - 1| <= 0.8 / n_max; inputs outside that range must come back exact through
+the direct kernels (the reference's np.power is exact for any radius, gen_atmosphere_stokes.py:265,
+gen_pressure_stokes.py:200).  Also: flipped (negative-stride) operands and whole-table PLM validation.
+"""
+import numpy as np
+import pytest
+
+from parity import TOL, rel_to_max, assert_structure
+
+pytestmark = pytest.mark.gpu
+
+
+def _mh():
+    import model_harmonics_b200 as mh
+    return mh
+
+
+def _launches():
+    from model_harmonics_b200 import _lib
+    return _lib.lib().mhb200_launch_count()
+
+
+@pytest.mark.parametrize('method', ['BC05', 'SW02'])
+@pytest.mark.parametrize('top_km', [48.0, 80.0, 150.0])
+def test_atmosphere_heights_inside_and_outside_the_guard(method, top_km):
+    """48 and 80 km stay on the moment path; 150 km trips the guard and is recomputed by the direct kernels."""
+    from oracle import stokes_oracle
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 60
+    lon, lat = syn.grid_axes(46, 90)
+    GPH, dP, geoid = syn.atmosphere_cube(37, 46, 90, seed=31)
+    GPH = GPH * (top_km / 48.0)
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=geoid, LOVE=syn.love_numbers(L), METHOD=method)
+    Y = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    O = stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    assert_structure(Y.clm, Y.slm, L, L)
+    e = rel_to_max(Y.clm, Y.slm, O.clm, O.slm)
+    print('%s top %g km: %.2e' % (method, top_km, e))
+    assert e <= TOL
+
+
+def test_geopotential_instead_of_height_is_still_exact():
+    """A caller passing geopotential (m^2/s^2, ~10x the height) lands far outside the expansion range."""
+    from oracle import stokes_oracle
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 40
+    lon, lat = syn.grid_axes(31, 60)
+    GPH, dP, geoid = syn.atmosphere_cube(9, 31, 60, seed=32)
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=geoid, LOVE=syn.love_numbers(L))
+    Y = mh.gen_atmosphere_stokes(GPH * 9.80665, dP, lon, lat, **kw)
+    O = stokes_oracle.gen_atmosphere_stokes(GPH * 9.80665, dP, lon, lat, **kw)
+    assert rel_to_max(Y.clm, Y.slm, O.clm, O.slm) <= TOL
+
+
+def test_guard_is_per_call_and_moment_and_direct_paths_agree(monkeypatch):
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 60
+    lon, lat = syn.grid_axes(46, 90)
+    GPH, dP, geoid = syn.atmosphere_cube(12, 46, 90, seed=33)
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=geoid, LOVE=syn.love_numbers(L))
+    a = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    mh.gen_atmosphere_stokes(GPH * 5.0, dP, lon, lat, **kw)          # trips the guard
+    b = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)            # the flag does not leak into the next call
+    assert np.array_equal(a.clm, b.clm) and np.array_equal(a.slm, b.slm)
+    monkeypatch.setenv('MHB200_MOMENTS', '0')
+    c = mh.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    assert rel_to_max(a.clm, a.slm, c.clm, c.slm) <= 1e-13
+    assert not np.array_equal(a.clm, c.clm)                          # they really are different kernels
+
+
+@pytest.mark.parametrize('L', [60, 200])
+def test_pressure_radius_spread_inside_and_outside_the_guard(L):
+    from oracle import stokes_oracle
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    lon, lat = syn.grid_axes(61, 120)
+    G, R = syn.surface_geometry(lon, lat, seed=34)
+    P = syn.pressure_fields(61, 120, 1, seed=34)[0]
+    LOVE = syn.love_numbers(L)
+    rng = np.random.default_rng(35)
+    # metres of extra random radius: 60 km is inside the guard at LMAX 60 (82 km) and outside at LMAX 200
+    # (25 km); 200 km is outside at both
+    for spread in (0.0, 60.0e3, 200.0e3):
+        R2 = R + spread * rng.uniform(-1.0, 1.0, R.shape)
+        Y = mh.gen_pressure_stokes(P, G, R2, lon, lat, LMAX=L, LOVE=LOVE)
+        O = stokes_oracle.gen_pressure_stokes(P, G, R2, lon, lat, LMAX=L, LOVE=LOVE)
+        e = rel_to_max(Y.clm, Y.slm, O.clm, O.slm)
+        print('LMAX %d spread %g m: %.2e' % (L, spread, e))
+        assert e <= TOL
+
+
+def test_pressure_bad_radius_values_propagate_like_the_reference():
+    """A NaN radius must give NaN coefficients (np.power propagates it), not a silently finite answer."""
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    lon, lat = syn.grid_axes(31, 60)
+    G, R = syn.surface_geometry(lon, lat, seed=36)
+    P = syn.pressure_fields(31, 60, 1, seed=36)[0]
+    R = R.copy()
+    R[7, 11] = np.nan
+    Y = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=20, LOVE=syn.love_numbers(20))
+    assert np.isnan(Y.clm).any()
+
+
+def test_moment_path_runs_three_kernels_plus_two_guarded_stubs():
+    import torch
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    lon, lat = syn.grid_axes(46, 90)
+    GPH, dP, geoid = syn.atmosphere_cube(5, 46, 90, seed=37)
+    g, d = torch.from_numpy(GPH).cuda(), torch.from_numpy(dP).cuda()
+    kw = dict(LMAX=30, ELLIPSOID='WGS84', GEOID=geoid, LOVE=syn.love_numbers(30), as_numpy=False)
+    mh.atmosphere_stokes_batch(g[None], d[None], lon, lat, **kw)
+    n0 = _launches()
+    mh.atmosphere_stokes_batch(g[None], d[None], lon, lat, **kw)
+    assert _launches() - n0 == 5          # K_A, K_B, K_C + the direct ring / reduce kernels (exit at once)
+
+
+def test_flipped_views_are_accepted_like_the_reference():
+    """Negative-stride operands (P[::-1], GPH[:, ::-1]) -- ADVICE r1: torch.from_numpy rejects them."""
+    from oracle import stokes_oracle
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 30
+    LOVE = syn.love_numbers(L)
+    lon, lat = syn.grid_axes(46, 90)
+    G, R = syn.surface_geometry(lon, lat, seed=38)
+    P = syn.pressure_fields(46, 90, 1, seed=38)[0]
+    lat_r = lat[::-1]
+    Y = mh.gen_pressure_stokes(P[::-1, :], G[::-1, :], R[::-1, :], lon, lat_r, LMAX=L, LOVE=LOVE)
+    O = stokes_oracle.gen_pressure_stokes(P[::-1, :], G[::-1, :], R[::-1, :], lon, lat_r, LMAX=L, LOVE=LOVE)
+    assert rel_to_max(Y.clm, Y.slm, O.clm, O.slm) <= TOL
+    GPH, dP, geoid = syn.atmosphere_cube(4, 46, 90, seed=39)
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', LOVE=LOVE)
+    Y = mh.gen_atmosphere_stokes(GPH[:, ::-1], dP[:, ::-1], lon, lat_r, GEOID=geoid[::-1], **kw)
+    O = stokes_oracle.gen_atmosphere_stokes(GPH[:, ::-1], dP[:, ::-1], lon, lat_r, GEOID=geoid[::-1], **kw)
+    assert rel_to_max(Y.clm, Y.slm, O.clm, O.slm) <= TOL
+
+
+def test_plm_table_differing_in_unsampled_entries_is_honoured():
+    """a caller table that differs from the standard one anywhere must be used as given."""
+    from oracle import stokes_oracle
+    from oracle.gravtk_standin import plm_holmes
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 40
+    LOVE = syn.love_numbers(L)
+    lon, lat = syn.grid_axes(61, 120)
+    G, R = syn.surface_geometry(lon, lat, seed=40)
+    P = syn.pressure_fields(61, 120, 1, seed=40)[0]
+    PLM, _ = plm_holmes(L, np.cos(np.radians(90.0 - lat)))
+    PLM2 = PLM.copy()
+    PLM2[17, 5, :] = 0.0                  # one filtered (l, m) row: not among the entries round 1 sampled
+    PLM2[33, 21, 30] *= 1.001
+    Y = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, PLM=PLM2, LOVE=LOVE)
+    O = stokes_oracle.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, PLM=PLM2, LOVE=LOVE)
+    assert rel_to_max(Y.clm, Y.slm, O.clm, O.slm) <= TOL
+    assert Y.clm[17, 5] == 0.0 and Y.slm[17, 5] == 0.0
+    # and the standard table still takes the on-the-fly path with identical results to PLM=None
+    A = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, PLM=PLM, LOVE=LOVE)
+    B = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, LOVE=LOVE)
+    assert np.array_equal(A.clm, B.clm) and np.array_equal(A.slm, B.slm)

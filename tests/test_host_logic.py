@@ -166,3 +166,46 @@ def test_harmonics_ascii_round_trip(tmp_path):
     assert len(path.read_text().splitlines()[0].split()) == 4
     W = _compat.harmonics().from_ascii(path, date=False)
     assert np.allclose(W.clm, Y.clm, rtol=1e-12, atol=0.0)
+
+
+def test_moment_schedule_probe_partitions_units_and_slots():
+    """Static schedule of the contracted-moment atmosphere kernel (csrc/stokes_moments.cu)."""
+    import ctypes
+    from model_harmonics_b200 import _lib
+    L = _lib.lib()
+    for nb, nrings, nchunks, max_ctas in [(1, 721, 6, 296), (8, 721, 6, 296), (1, 46, 1, 296), (3, 7, 2, 5),
+                                          (2, 90, 6, 296), (1, 1, 1, 296)]:
+        cu = (ctypes.c_int * (max_ctas + 1))()
+        cs = (ctypes.c_int * max_ctas)()
+        fs = (ctypes.c_int * (nb + 1))()
+        ns = ctypes.c_int(0)
+        ncta = L.mhb200_moment_schedule_probe(nb, nrings, nchunks, max_ctas, cu, cs, fs, max_ctas + 1,
+                                              ctypes.byref(ns))
+        units = nb * nrings * nchunks
+        assert ncta == min(max_ctas, units)
+        assert cu[0] == 0 and cu[ncta] == units
+        spans = [cu[b + 1] - cu[b] for b in range(ncta)]
+        assert min(spans) >= 1 and max(spans) - min(spans) <= 1          # equal split
+        # slots: one per (CTA, ring) pair; consecutive and grouped by field
+        slot = 0
+        rings_of_field = [set() for _ in range(nb)]
+        for b in range(ncta):
+            assert cs[b] == slot
+            rings = sorted(set(u // nchunks for u in range(cu[b], cu[b + 1])))
+            slot += len(rings)
+            for r in rings:
+                rings_of_field[r // nrings].add(r % nrings)
+        assert ns.value == slot
+        assert fs[0] == 0 and fs[nb] == slot
+        assert all(fs[t] <= fs[t + 1] for t in range(nb))
+        assert all(len(s) == nrings for s in rings_of_field)
+        assert slot <= nb * nrings + ncta
+
+
+def test_standard_plm_table_matches_the_oracle_table_bitwise():
+    from model_harmonics_b200 import _compat
+    from oracle.gravtk_standin import plm_holmes
+    x = np.cos(np.radians(90.0 - np.linspace(90.0, -90.0, 19)))
+    mine = _compat.plm_table(30, 17, x)
+    ref, _ = plm_holmes(30, x)
+    assert np.array_equal(mine, ref[:, :18, :])

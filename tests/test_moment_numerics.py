@@ -57,3 +57,131 @@ def test_truncation_bound_of_the_design_document():
     bound = lambda n, d: (n * d) ** NMOM / math.factorial(NMOM)
     assert bound(64, 0.007) < 1.0e-16          # levels to ~50 km
     assert bound(64, 0.016) < 1.0e-13          # levels to ~100 km
+
+
+# ---------------------------------------------------------------------------------------------------
+# Contracted-moment form (model_harmonics_b200/csrc/stokes_moments.cu): the binomial expansion is applied
+# AFTER the Fourier and Legendre sums, around a per-ring expansion point r0(h):
+#   C_lm = D_l sum_j C(l + n0, j) sum_h w_h P_lm(x_h) r0(h)^(l + n0) sum_p e^{i m phi_p} M_j[h, p]
+# Emulated here in NumPy, in the kernels' order of summation, against the oracle.
+# ---------------------------------------------------------------------------------------------------
+def _binom(nmom, L, off):
+    E = np.zeros((nmom, L + 1))
+    for l in range(L + 1):
+        for j in range(min(nmom, l + off + 1)):
+            E[j, l] = float(math.comb(l + off, j))
+    return E
+
+
+def _contract_moments(M, r0, w, PLM, eul, dfactor, L, off, scale):
+    F = np.einsum('mp,jhp->hmj', eul, M)
+    E = _binom(M.shape[0], L, off)
+    clm = np.zeros((L + 1, L + 1))
+    slm = np.zeros((L + 1, L + 1))
+    for l in range(L + 1):
+        pw = w * r0**(l + off)
+        G = np.einsum('mh,hmj->mj', PLM[l, :l + 1, :] * pw[None, :], F[:, :l + 1, :])
+        y = scale * dfactor[l] * (G @ E[:, l])
+        clm[l, :l + 1], slm[l, :l + 1] = y.real, y.imag
+    return clm, slm
+
+
+def _atmosphere_emulation(GPH, dP, lon, lat, L, geoid, LOVE, method, hc=24000.0):
+    from oracle import stokes_oracle as so
+    from oracle.gravtk_standin import plm_holmes, units
+    phi, th = np.radians(lon), np.radians(90.0 - lat)
+    a_axis, flat, rad_e, ecc1 = so.ellipsoid_constants('WGS84')
+    dfactor = units(lmax=L, a_axis=100.0 * a_axis, flat=flat).spatial(*LOVE).mmwe
+    w = np.sin(th) * np.abs(phi[1] - phi[0]) * np.abs(th[1] - th[0])
+    PLM, _ = plm_holmes(L, np.cos(th))
+    st, ct = np.sin(th), np.cos(th)
+    N = a_axis / np.sqrt(1.0 - ecc1**2 * ct**2)
+    M = np.zeros((NMOM,) + GPH.shape[1:])
+    dmax = 0.0
+    if method == 'BC05':
+        off, scale = 2, -1.0
+        r0 = np.sqrt((N * st)**2 + (N * (1 - ecc1**2) * ct)**2) / rad_e + hc / rad_e
+        a1 = 1.0 - 0.002644 * np.cos(2.0 * th)
+        a2 = (1.0 - 0.0089 * np.cos(2.0 * th)) / 6.245e6
+        gs = 9.780356 * (1.0 + 5.2885e-3 * ct**2 - 5.9e-6 * np.cos(2.0 * th)**2)
+        g1 = -gs * 2.0 * (1.006803 - 0.06706 * ct**2) / rad_e
+        g2 = 3.0 * gs / rad_e**2
+        for k in range(GPH.shape[0]):
+            z = GPH[k]
+            H = z * (a1[:, None] + a2[:, None] * z)
+            S = ((N[:, None] + geoid + H) * st[:, None])**2 + ((N[:, None] * (1 - ecc1**2) + geoid + H) * ct[:, None])**2
+            q = dP[k] / (gs[:, None] + H * (g1[:, None] + g2[:, None] * H))
+            d = np.sqrt(S) / (rad_e * r0[:, None]) - 1.0
+            dmax = max(dmax, float(np.abs(d).max()))
+            t = q.copy()
+            for j in range(NMOM):
+                M[j] += t
+                t = t * d
+    else:
+        off, scale = 4, -1.0 / 9.80665
+        r0 = np.full(len(th), 1.0 + hc / rad_e)
+        for k in range(GPH.shape[0]):
+            d = (rad_e / (rad_e - GPH[k]) + geoid / rad_e) / r0[:, None] - 1.0
+            dmax = max(dmax, float(np.abs(d).max()))
+            t = dP[k].copy()
+            for j in range(NMOM):
+                M[j] += t
+                t = t * d
+    eul = np.exp(1j * np.outer(np.arange(L + 1), phi))
+    return _contract_moments(M, r0, w, PLM, eul, dfactor, L, off, scale) + (dmax,)
+
+
+@pytest.mark.parametrize('method', ['BC05', 'SW02'])
+@pytest.mark.parametrize('top_scale', [1.0, 80.0 / 48.0])
+def test_contracted_moment_atmosphere_matches_oracle(method, top_scale):
+    from oracle import stokes_oracle as so
+    from model_harmonics_b200 import testing as syn
+    L = 60
+    LOVE = syn.love_numbers(L)
+    lon, lat = syn.grid_axes(46, 90)
+    GPH, dP, geoid = syn.atmosphere_cube(37, 46, 90, seed=5)
+    GPH = GPH * top_scale
+    ref = so.gen_atmosphere_stokes(GPH, dP, lon, lat, LMAX=L, ELLIPSOID='WGS84', GEOID=geoid, LOVE=LOVE, METHOD=method)
+    clm, slm, dmax = _atmosphere_emulation(GPH, dP, lon, lat, L, geoid, LOVE, method)
+    # inside the guard of the kernel (stokes_moments.cu: n_max |d| <= 0.8)
+    assert dmax * (L + (2 if method == 'BC05' else 4)) <= 0.8
+    scale = max(np.abs(ref.clm).max(), np.abs(ref.slm).max())
+    err = max(np.abs(clm - ref.clm).max(), np.abs(slm - ref.slm).max()) / scale
+    assert err <= 1.0e-13, err
+
+
+def test_contracted_moment_pressure_lmax360_matches_oracle():
+    """Per-ring expansion point = mid-range of R / rad_e over the ring (pressure_moment_kernel)."""
+    from oracle import stokes_oracle as so
+    from oracle.gravtk_standin import plm_holmes, units
+    from model_harmonics_b200 import testing as syn
+    L = 360
+    LOVE = syn.love_numbers(L)
+    lon, lat = syn.grid_axes(31, 60)
+    G, R = syn.surface_geometry(lon, lat, seed=5)
+    P = syn.pressure_fields(31, 60, 1, seed=5)[0] + 1.0e4
+    ref = so.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, LOVE=LOVE)
+    phi, th = np.radians(lon), np.radians(90.0 - lat)
+    fac = units(lmax=L).spatial(*LOVE)
+    rad_e = fac.rad_e / 100.0
+    w = np.sin(th) * np.abs(phi[1] - phi[0]) * np.abs(th[1] - th[0])
+    PLM, _ = plm_holmes(L, np.cos(th))
+    r = R / rad_e
+    r0 = 0.5 * (r.max(axis=1) + r.min(axis=1))
+    d = r / r0[:, None] - 1.0
+    assert np.abs(d).max() * (L + 2) <= 0.8
+    M = np.zeros((NMOM,) + P.shape)
+    t = P / G
+    for j in range(NMOM):
+        M[j] = t
+        t = t * d
+    eul = np.exp(1j * np.outer(np.arange(L + 1), phi))
+    clm, slm = _contract_moments(M, r0, w, PLM, eul, fac.mmwe, L, 2, 1.0)
+    scale = max(np.abs(ref.clm).max(), np.abs(ref.slm).max())
+    err = max(np.abs(clm - ref.clm).max(), np.abs(slm - ref.slm).max()) / scale
+    assert err <= 1.0e-13, err
+
+
+def test_guard_bound_of_the_contracted_moment_kernels():
+    # truncated tail (n |d|)^16 / 16! at the guard n |d| = 0.8
+    assert 0.8 ** NMOM / math.factorial(NMOM) < 2.0e-15
