@@ -19,6 +19,12 @@
  *     (zeros where m > l);
  *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); the
  *     calls do not synchronise;
+ *   - re-entrancy: a plan is immutable after creation apart from internally locked caches, and every
+ *     per-call mutable buffer (partial sums, staged field scales / degree factors, the moment path's
+ *     Fourier sums and guard flag) lives in the CALLER's workspace.  Calls may therefore run
+ *     concurrently from several threads and streams on one plan as long as each stream in flight
+ *     has its own workspace (same-stream calls may share one).  The host-buffer entry
+ *     mhb200_atmosphere_stokes_host owns device staging cubes per plan and is serialised per plan;
  *   - return value: MHB200_OK or a negative MHB200_E* code;
  *     mhb200_last_error() gives a thread-local message.
  *   - there is no CPU fallback: without a CUDA device every call fails.

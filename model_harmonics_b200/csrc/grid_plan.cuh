@@ -91,10 +91,6 @@ struct mhb200_plan {
   double* out_pinned = nullptr;
   int* lb_first_tile_dev = nullptr;
   std::vector<int> lb_first_tile;
-  // per-call staging (field scales, long degree-factor vectors), grown on demand
-  double* stage_dev = nullptr;
-  size_t stage_doubles = 0;
-  size_t stage_reserved = 0;   // doubles at the front of the staging buffer used by field scales
   std::mutex mu;
   mhb::MomentPlan* mom = nullptr;   // contracted-moment path (null: grid not eligible)
 };

@@ -1276,6 +1276,8 @@ HostSchedule make_schedule(int nlb, int nmb, int nchunks, int max_ctas, int fold
 int build_schedule_range(mhb200_plan* pl, Variant& v, Schedule& sc, int nbatch, int nlev, int mode, int h0,
                          int h1) {
   if (sc.nbatch == nbatch && sc.nlev == nlev && sc.mode == mode && sc.h0 == h0 && sc.h1 == h1) return MHB200_OK;
+  // a kernel enqueued on another stream may still be reading the old tables
+  if (sc.segs_dev) MHB_CUDA(cudaDeviceSynchronize());
   free_schedule(sc);
   const HostSchedule hs = make_schedule(pl->nlb, pl->nmb, v.nchunks, pl->num_sms * v.ctas_per_sm, pl->fold, nbatch,
                                         nlev, mode, h0, h1);
@@ -1331,25 +1333,11 @@ int pick_variant(const mhb200_plan* pl, int mode) {
   return v;
 }
 
-int stage(mhb200_plan* pl, const double* host, size_t n, size_t offset, cudaStream_t st) {
-  if (offset + n > pl->stage_doubles) {
-    set_err("internal: staging buffer too small");
-    return MHB200_EINVAL;
-  }
-  MHB_CUDA(cudaMemcpyAsync(pl->stage_dev + offset, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
-  return MHB200_OK;
-}
-
-int ensure_stage(mhb200_plan* pl, size_t n) {
-  if (n <= pl->stage_doubles) return MHB200_OK;
-  if (pl->stage_dev) {
-    MHB_CUDA(cudaDeviceSynchronize());
-    cudaFree(pl->stage_dev);
-    pl->stage_dev = nullptr;
-    pl->stage_doubles = 0;
-  }
-  MHB_CUDA(cudaMalloc((void**)&pl->stage_dev, n * sizeof(double)));
-  pl->stage_doubles = n;
+// Per-call host operands (field scales, degree factors longer than the kernel-parameter array) are staged in
+// the tail of the CALLER's workspace, so that calls on different streams (each with its own workspace) never
+// share mutable device state: layout [2 * nbatch field scales][lmax + 1 degree factors].
+int stage_copy(double* dst, const double* host, size_t n, cudaStream_t st) {
+  MHB_CUDA(cudaMemcpyAsync(dst, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
   return MHB200_OK;
 }
 
@@ -1373,7 +1361,7 @@ int launch_ring(const GridParams& gp, const Variant& v, cudaStream_t st) {
 }
 
 int finish_reduce(mhb200_plan* pl, const Variant& v, const double* dfactor, int nbatch, double* slots,
-                  double* clm, double* slm, cudaStream_t st, const int* run_flag = nullptr) {
+                  double* clm, double* slm, cudaStream_t st, const int* run_flag, double* df_stage) {
   ReduceParams q;
   q.run_flag = run_flag;
   q.dfactor_dev = nullptr;
@@ -1381,9 +1369,8 @@ int finish_reduce(mhb200_plan* pl, const Variant& v, const double* dfactor, int 
     for (int l = 0; l <= pl->lmax; ++l) q.dfactor[l] = dfactor[l];
   } else {
     int rc;
-    if ((rc = ensure_stage(pl, (size_t)pl->lmax + 1 + pl->stage_reserved)) != MHB200_OK) return rc;
-    if ((rc = stage(pl, dfactor, (size_t)pl->lmax + 1, pl->stage_reserved, st)) != MHB200_OK) return rc;
-    q.dfactor_dev = pl->stage_dev + pl->stage_reserved;
+    if ((rc = stage_copy(df_stage, dfactor, (size_t)pl->lmax + 1, st)) != MHB200_OK) return rc;
+    q.dfactor_dev = df_stage;
   }
   q.lmax = pl->lmax;
   q.mmax = pl->mmax;
@@ -1631,9 +1618,6 @@ int mhb200_plan_create(mhb200_plan** out, int device, int nlat, int nlon, int lm
   pl->nlb = (lmax + LBLK) / LBLK;
   pl->nmb = (mmax + MBLK) / MBLK;
   pl->Mpad = pl->nmb * MBLK;
-  pl->stage_dev = nullptr;
-  pl->stage_doubles = 0;
-  pl->stage_reserved = 0;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) {
     set_err("mhb200_plan_create: cannot query the SM count of device %d", device);
@@ -1773,7 +1757,6 @@ int mhb200_plan_destroy(mhb200_plan* pl) {
   if (pl->done_ev) cudaEventDestroy(pl->done_ev);
   if (pl->out_dev) cudaFree(pl->out_dev);
   if (pl->out_pinned) cudaFreeHost(pl->out_pinned);
-  if (pl->stage_dev) cudaFree(pl->stage_dev);
   delete pl;
   return MHB200_OK;
 }
@@ -1788,16 +1771,24 @@ static size_t host_slots_bytes(const mhb200_plan* pl, int nbands) {
   return ((size_t)nbands * max_segments(pl, 1) * SLOT_DOUBLES * sizeof(double) + 255) & ~(size_t)255;
 }
 
+static size_t stage_bytes(const mhb200_plan* pl, int nbatch) {
+  return ((2 * (size_t)nbatch + (size_t)pl->lmax + 1) * sizeof(double) + 255) & ~(size_t)255;
+}
+// staging area of a workspace (see stage_copy)
+static double* stage_area(const mhb200_plan* pl, void* workspace, size_t slots, int nbatch, int launches) {
+  return (double*)((char*)workspace + slots + moment_workspace_bytes(pl, nbatch, launches));
+}
+
 size_t mhb200_grid_workspace_bytes(const mhb200_plan* pl, int nbatch, int nlev) {
   (void)nlev;
   if (!pl || nbatch < 1) return 0;
-  return slots_bytes(pl, nbatch) + moment_workspace_bytes(pl, nbatch, 1);
+  return slots_bytes(pl, nbatch) + moment_workspace_bytes(pl, nbatch, 1) + stage_bytes(pl, nbatch);
 }
 
 size_t mhb200_host_workspace_bytes(const mhb200_plan* pl, int nbands) {
   if (!pl || nbands < 1) return 0;
   nbands = std::min(nbands, MAX_PARTS);
-  return host_slots_bytes(pl, nbands) + moment_workspace_bytes(pl, 1, nbands);
+  return host_slots_bytes(pl, nbands) + moment_workspace_bytes(pl, 1, nbands) + stage_bytes(pl, 1);
 }
 
 int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const int64_t Ps[3], const double* G,
@@ -1819,7 +1810,7 @@ int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const in
   Variant& v = pl->var[pick_variant(pl, MODE_PRESSURE)];
   int rc;
   if ((rc = build_schedule(pl, v, nbatch, 0, MODE_PRESSURE)) != MHB200_OK) return rc;
-  pl->stage_reserved = 0;
+  double* stg = stage_area(pl, workspace, slots_bytes(pl, nbatch), nbatch, 1);
   GridParams gp;
   fill_plan_params(pl, v, gp);
   gp.plm_table = plm_table;
@@ -1838,9 +1829,8 @@ int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const in
   if (moment_pressure_eligible(pl, plm_table)) {
     const double* df_dev = nullptr;
     if (pl->lmax + 1 > DF_MAX) {
-      if ((rc = ensure_stage(pl, (size_t)pl->lmax + 1)) != MHB200_OK) return rc;
-      if ((rc = stage(pl, dfactor, (size_t)pl->lmax + 1, 0, st)) != MHB200_OK) return rc;
-      df_dev = pl->stage_dev;
+      if ((rc = stage_copy(stg + 2 * (size_t)nbatch, dfactor, (size_t)pl->lmax + 1, st)) != MHB200_OK) return rc;
+      df_dev = stg + 2 * (size_t)nbatch;
     }
     const int* flag = nullptr;
     rc = moment_pressure_run(pl, P, gp.Ps, G, gp.Gs, R, gp.Rs, nbatch, rad_e, dfactor, df_dev, clm_out, slm_out,
@@ -1849,7 +1839,7 @@ int mhb200_pressure_stokes_f64(const mhb200_plan* cpl, const double* P, const in
     gp.run_flag = flag;
   }
   if ((rc = launch_ring<MODE_PRESSURE, double>(gp, v, st)) != MHB200_OK) return rc;
-  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st, gp.run_flag);
+  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st, gp.run_flag, stg + 2 * (size_t)nbatch);
 }
 
 int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH, const void* dP,
@@ -1876,10 +1866,8 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
   Variant& v = pl->var[pick_variant(pl, mode)];
   int rc;
   if ((rc = build_schedule(pl, v, nbatch, nlev, mode)) != MHB200_OK) return rc;
-  const size_t nl = (size_t)pl->lmax + 1;
-  pl->stage_reserved = field_scale ? 2 * (size_t)nbatch : 0;
-  if ((rc = ensure_stage(pl, nl + 2 * (size_t)nbatch)) != MHB200_OK) return rc;
-  if (field_scale && (rc = stage(pl, field_scale, 2 * (size_t)nbatch, 0, st)) != MHB200_OK) return rc;
+  double* stg = stage_area(pl, workspace, slots_bytes(pl, nbatch), nbatch, 1);
+  if (field_scale && (rc = stage_copy(stg, field_scale, 2 * (size_t)nbatch, st)) != MHB200_OK) return rc;
   GridParams gp;
   fill_plan_params(pl, v, gp);
   gp.plm_table = plm_table;
@@ -1887,7 +1875,7 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
   gp.GPH = GPH;
   gp.dP = dP;
   gp.batch_stride = batch_stride;
-  gp.field_scale = field_scale ? pl->stage_dev : nullptr;
+  gp.field_scale = field_scale ? stg : nullptr;
   gp.geoid = geoid;
   gp.geo_s0 = geoid ? geoid_stride[0] : 0;
   gp.geo_s1 = geoid ? geoid_stride[1] : 0;
@@ -1914,7 +1902,7 @@ int mhb200_atmosphere_stokes(const mhb200_plan* cpl, int dtype, const void* GPH,
     rc = (dtype == MHB200_F64) ? launch_ring<MODE_ATM_SW02, double>(gp, v, st)
                                : launch_ring<MODE_ATM_SW02, float>(gp, v, st);
   if (rc != MHB200_OK) return rc;
-  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st, gp.run_flag);
+  return finish_reduce(pl, v, dfactor, nbatch, gp.slots, clm_out, slm_out, st, gp.run_flag, stg + 2 * (size_t)nbatch);
 }
 
 
@@ -1968,7 +1956,6 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
   // the previous call's kernels (on `stream`) must be done with the device cubes before they are overwritten
   MHB_CUDA(cudaEventRecord(pl->done_ev, st));
   MHB_CUDA(cudaStreamWaitEvent(pl->copy_stream, pl->done_ev, 0));
-  pl->stage_reserved = 0;
 
   GridParams gp;
   ReduceParams q;
@@ -2035,9 +2022,9 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
   if (pl->lmax + 1 <= DF_MAX) {
     for (int l = 0; l <= pl->lmax; ++l) q.dfactor[l] = dfactor[l];
   } else {
-    if ((rc = ensure_stage(pl, (size_t)pl->lmax + 1)) != MHB200_OK) return rc;
-    if ((rc = stage(pl, dfactor, (size_t)pl->lmax + 1, 0, st)) != MHB200_OK) return rc;
-    q.dfactor_dev = pl->stage_dev;
+    double* stg = stage_area(pl, workspace, host_slots_bytes(pl, nbands), 1, nbands);
+    if ((rc = stage_copy(stg + 2, dfactor, (size_t)pl->lmax + 1, st)) != MHB200_OK) return rc;
+    q.dfactor_dev = stg + 2;
   }
   q.lmax = pl->lmax;
   q.mmax = pl->mmax;

@@ -5,8 +5,9 @@
 //   model_harmonics/gen_pressure_stokes.py:194-206      per-degree power pass + complex einsum
 //
 // Per latitude ring h the radius ratio is written r = r0(h) (1 + d) with a ring-wide expansion
-// point r0(h), so that  r^n = r0^n sum_j C(n, j) d^j  and the per-degree radial factor needs only
-// NMOM = 16 moments per column,
+// point r0(h), so that  r^n = r0^n sum_j C(n, j) d^j  (BC05 expands in e = (1 + d)^2 - 1 instead,
+// r^n = r0^n sum_j C(n/2, j) e^j, which spares the square root of the geocentric radius)
+// and the per-degree radial factor needs only NMOM = 16 moments per column,
 //   atmosphere:  M_j[p] = sum_k (dp_k / gamma_k) d_k^j        pressure:  M_j[p] = (P/G) d^j .
 // The binomial expansion, the Fourier sum over longitude and the Legendre sum over latitude are all
 // linear, so they commute; the expansion is applied LAST, once per coefficient:
@@ -126,6 +127,23 @@ __device__ __forceinline__ void sqrt_t(const double (&a)[W], double (&g)[W]) {
   for (int i = 0; i < W; ++i) g[i] = fma(r[i], h[i], g[i]);
 }
 
+// The kernels expand around r0 through a rounded reciprocal c (d = R c - 1, c ~ 1 / (rad_e r0)), so the
+// expansion point they really use is 1 / (rad_e c), which differs from the double r0 that K_B raises to the
+// n-th power by a relative q ~ 1e-16 -- systematic over a ring and amplified by n.  q is computed here to
+// ~1e-32 with error-free products, stored per slot, and K_B multiplies r0^n by (1 - n q).
+//   one_plus_q(a, b, c): q with a * b * c = 1 + q;  the squared form: (a * b)^2 * c = 1 + q
+__device__ __forceinline__ double residual3(double a, double b, double c) {
+  const double ab = a * b, ab_lo = fma(a, b, -ab);
+  const double p = ab * c, p_lo = fma(ab, c, -p) + ab_lo * c;
+  return (p - 1.0) + p_lo;
+}
+__device__ __forceinline__ double residual_sq(double a, double b, double c) {
+  const double ab = a * b, ab_lo = fma(a, b, -ab);
+  const double s = ab * ab, s_lo = fma(ab, ab, -s) + 2.0 * ab * ab_lo;
+  const double p = s * c, p_lo = fma(s, c, -p) + s_lo * c;
+  return (p - 1.0) + p_lo;
+}
+
 // m[j] += w d^j, j < 16:  7 products + 16 accumulates
 __device__ __forceinline__ void accumulate16(double (&m)[NMOMC], double w, double d) {
   const double d2 = d * d, d3 = d2 * d, d4 = d2 * d2;
@@ -170,6 +188,7 @@ struct AtmMomParams {
   const double* trig;          // A fragments [nchunks * 16][16 row tiles][32 lanes], order block 0
   double* F;                   // [slot][64 orders][cs][16 moments]
   double* slot_r0;
+  double* slot_q;              // correction of r0^n per unit of n (see residual3)
   int* slot_ring;
   int* flag;
   double rad_e, inv_rad, hc;
@@ -178,20 +197,23 @@ struct AtmMomParams {
 
 struct ColumnC {
   // BC05: a1, a2 orthometric-height factors (field scale folded in), st, ct, g0..g2 normal gravity
-  // gam = g0 + H (g1 + g2 H), NG = N + geoid, NG1 = N (1 - e^2) + geoid, cinv = 1 / (rad_e r0)
+  // gam = g0 + H (g1 + g2 H), NG = N + geoid, NG1 = N (1 - e^2) + geoid, cinv = 1 / (rad_e r0)^2
   // SW02: rad_e, sg, inv_r0, c0 = geoid / (rad_e r0) - 1
   double a1, a2, st, ct, g0, g1, g2, NG, NG1, cinv;
   double rad_e, sg, inv_r0, c0;
 };
 
 // (w, d) of W (level, column) elements:  w = dp / gamma (BC05) or dp (SW02; 1/g0 is applied at the flush),
-// d = r / r0 - 1.  Reference lines: gen_atmosphere_stokes.py:222-238 (BC05), :258-260 (SW02).
+// d = (r / r0)^2 - 1 (BC05) or r / r0 - 1 (SW02).  Reference lines: gen_atmosphere_stokes.py:222-238 (BC05), :258-260 (SW02).
 // X^2 + Y^2 is formed as ((N + geoid + H) sin(theta))^2: cos^2(phi) + sin^2(phi) differs from 1 by rounding only.
 template <int MODE, int W>
 __device__ __forceinline__ void moment_elements(const double (&z)[W], const double (&dpv)[W], const ColumnC& c,
                                                 double (&w)[W], double (&d)[W]) {
   if (MODE == MHB200_METHOD_BC05) {
-    double H[W], S[W], R[W], gam[W];
+    // BC05 expands in e = (R / (rad_e r0))^2 - 1 = 2 d + d^2 with the generalised binomial series
+    // r^n = r0^n (1 + e)^(n/2) = r0^n sum_j C(n/2, j) e^j  (same convergence: (n/2) e ~ n d) -- R^2 is what
+    // the geometry produces, so no square root is needed
+    double H[W], S[W], gam[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) H[i] = z[i] * fma(c.a2, z[i], c.a1);
 #pragma unroll
@@ -200,10 +222,9 @@ __device__ __forceinline__ void moment_elements(const double (&z)[W], const doub
       S[i] = fma(Zz, Zz, As * As);
       gam[i] = fma(H[i], fma(c.g2, H[i], c.g1), c.g0);
     }
-    sqrt_t<W>(S, R);
     div_t<W>(dpv, gam, w);
 #pragma unroll
-    for (int i = 0; i < W; ++i) d[i] = fma(R[i], c.cinv, -1.0);
+    for (int i = 0; i < W; ++i) d[i] = fma(S[i], c.cinv, -1.0);
   } else {
     double den[W], num[W], t[W];
 #pragma unroll
@@ -325,7 +346,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       sp = __ldg(p.field_scale + 2 * (p.t0 + t) + 1);
     }
     ColumnC cc;
-    double r0;
+    double r0, qs;
     if (MODE == MHB200_METHOD_BC05) {
       const double* rt = p.ring_tab + h;
       const double N = __ldg(rt + 2 * p.nlat), N1 = __ldg(rt + 3 * p.nlat);
@@ -339,7 +360,9 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       cc.g2 = (3.0 * gs) * (p.inv_rad * p.inv_rad);
       const double ex = N * cc.st, ez = N1 * cc.ct;
       r0 = sqrt(fma(ez, ez, ex * ex)) * p.inv_rad + p.hc * p.inv_rad;
-      cc.cinv = 1.0 / (p.rad_e * r0);
+      const double rr = p.rad_e * r0;
+      cc.cinv = 1.0 / (rr * rr);
+      qs = 0.5 * residual_sq(r0, p.rad_e, cc.cinv);     // (r0 rad_e)^2 cinv = 1 + q;  r0'^n = r0^n (1 + q)^(-n/2)
       cc.NG = N + geo;
       cc.NG1 = N1 + geo;
       cc.rad_e = cc.sg = cc.inv_r0 = cc.c0 = 0.0;
@@ -349,6 +372,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       cc.sg = sg;
       cc.inv_r0 = 1.0 / r0;
       cc.c0 = fma(geo * p.inv_rad, cc.inv_r0, -1.0);
+      qs = residual3(r0, 1.0, cc.inv_r0);               // r0 inv_r0 = 1 + q
       cc.a1 = cc.a2 = cc.st = cc.ct = cc.g0 = cc.g1 = cc.g2 = cc.NG = cc.NG1 = cc.cinv = 0.0;
     }
 
@@ -454,6 +478,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
         }
       if (tid == 0) {
         p.slot_r0[slot] = r0;
+        p.slot_q[slot] = qs;
         p.slot_ring[slot] = h;
       }
       ++slot;
@@ -482,6 +507,7 @@ struct PressMomParams {
   const double* trig;          // A fragments [nmb][nks_total][16 row tiles][32 lanes]
   double* F;                   // [slot = field * nlat + ring][Frows orders][cs][16 moments]
   double* slot_r0;
+  double* slot_q;
   int* slot_ring;
   int* flag;
   double rad_e, inv_rad;
@@ -640,6 +666,7 @@ __global__ void __launch_bounds__(256, 2) pressure_moment_kernel(const __grid_co
           *reinterpret_cast<double2*>(Fs + cs * 16 + nt * 8) = make_double2(facc[rr][cs][nt][0], facc[rr][cs][nt][1]);
       if (mb == 0 && tid == rr) {
         p.slot_r0[slot] = ringc[rr];
+        p.slot_q[slot] = residual3(ringc[rr], p.rad_e, ringc[PNR + rr]);     // r0 rad_e c = 1 + q
         p.slot_ring[slot] = h;
       }
     }
@@ -660,6 +687,7 @@ struct LegParams {
   const double *f1, *f2, *pmm, *sq, *rescale, *x, *w, *ckpt;
   const double* F;
   const double* slot_r0;
+  const double* slot_q;
   const int* slot_ring;
   int field_slot[NB_SUB + 1];
   double* G;
@@ -699,6 +727,7 @@ __global__ void __launch_bounds__(128) legendre_moment_kernel(const __grid_const
     const bool valid = (s < s1);
     const int h = valid ? q.slot_ring[s] : 0;
     const double rho = valid ? q.slot_r0[s] : 1.0;
+    const double qs = valid ? q.slot_q[s] : 0.0;
     const double xv = q.x[h], wh = q.w[h];
     const double rs = q.rescale[(size_t)h * q.Mpad + m];
     // recursion state: (p2, p1) = values at degrees (l - 2, l - 1) for the next degree l
@@ -741,7 +770,8 @@ __global__ void __launch_bounds__(128) legendre_moment_kernel(const __grid_const
           double v = 0.0;
           if (l >= m && l <= lend) {
             const double cur = step();
-            v = __dmul_rn(__dmul_rn(cur, rs), wh) * rp;
+            // r0'^n = r0^n (1 - n q): the expansion point K_A really used (see residual3)
+            v = (__dmul_rn(__dmul_rn(cur, rs), wh) * rp) * fma(-(double)(l + q.noff), qs, 1.0);
             rp *= rho;
           }
           T[ks * 64 + (dl >> 3) * 32 + ((((dl & 7) + ks) & 7) << 2) + k] = valid ? v : 0.0;
@@ -843,7 +873,7 @@ size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 // layout of the moment region of a workspace
 struct MomWs {
-  size_t flag, slot_r0, slot_ring, F, G, total;
+  size_t flag, slot_r0, slot_q, slot_ring, F, G, total;
 };
 MomWs mom_layout(const mhb200_plan* pl, size_t max_slots, size_t g_units) {
   MomWs w;
@@ -851,6 +881,8 @@ MomWs mom_layout(const mhb200_plan* pl, size_t max_slots, size_t g_units) {
   w.flag = o;
   o += 256;
   w.slot_r0 = o;
+  o = align256(o + max_slots * sizeof(double));
+  w.slot_q = o;
   o = align256(o + max_slots * sizeof(double));
   w.slot_ring = o;
   o = align256(o + max_slots * sizeof(int));
@@ -1059,16 +1091,18 @@ int moment_plan_create(mhb200_plan* pl, const double* phi) {
     }
   }
   mp->nunits = (int)unit_lm.size() / 2;
-  // binomial coefficients C(l + n0, j), n0 = 2 (BC05, pressure) and 4 (SW02)
+  // expansion coefficients C(a, j) = a (a - 1) ... (a - j + 1) / j!:
+  //   table 0: a = l + 2 (pressure, expansion in d)    table 1: a = l + 4 (SW02, in d)
+  //   table 2: a = (l + 2) / 2, generalised (BC05, expansion in e = (1 + d)^2 - 1)
   const int nl = pl->lmax + 1;
-  std::vector<double> E((size_t)2 * NMOMC * nl, 0.0);
-  for (int v = 0; v < 2; ++v)
+  std::vector<double> E((size_t)3 * NMOMC * nl, 0.0);
+  for (int v = 0; v < 3; ++v)
     for (int l = 0; l < nl; ++l) {
-      const int n = l + (v ? 4 : 2);
-      long double cnj = 1.0L;
+      const long double a = (v == 0) ? (long double)(l + 2) : (v == 1) ? (long double)(l + 4) : 0.5L * (l + 2);
+      long double caj = 1.0L;
       for (int j = 0; j < NMOMC; ++j) {
-        if (j > 0) cnj = cnj * (long double)(n - j + 1) / (long double)j;
-        E[((size_t)v * NMOMC + j) * nl + l] = (j <= n) ? (double)cnj : 0.0;
+        if (j > 0) caj = caj * (a - (long double)(j - 1)) / (long double)j;
+        E[((size_t)v * NMOMC + j) * nl + l] = (double)caj;
       }
     }
   int rc;
@@ -1203,13 +1237,15 @@ static int moment_atm_launch(mhb200_plan* pl, const MomCall& c, const MomWs& lay
   ap.trig = mp->trig;
   ap.F = (double*)(ws + lay.F);
   ap.slot_r0 = (double*)(ws + lay.slot_r0);
+  ap.slot_q = (double*)(ws + lay.slot_q);
   ap.slot_ring = (int*)(ws + lay.slot_ring);
   ap.flag = (int*)(ws + lay.flag);
   ap.rad_e = c.rad_e;
   ap.inv_rad = 1.0 / c.rad_e;
   ap.hc = MOM_CENTER_HEIGHT;
-  const int noff = (c.mode == MHB200_METHOD_BC05) ? 2 : 4;
-  const double bound = MOM_ND_BOUND / (double)(pl->lmax + noff);
+  // BC05: (n_max / 2) |e| <= 0.8, n = l + 2;  SW02: n_max |d| <= 0.8, n = l + 4
+  const double bound = (c.mode == MHB200_METHOD_BC05) ? 2.0 * MOM_ND_BOUND / (double)(pl->lmax + 2)
+                                                      : MOM_ND_BOUND / (double)(pl->lmax + 4);
   unsigned long long bits;
   memcpy(&bits, &bound, 8);
   ap.dbound_hi = (unsigned)(bits >> 32);
@@ -1217,7 +1253,9 @@ static int moment_atm_launch(mhb200_plan* pl, const MomCall& c, const MomWs& lay
 }
 
 // K_B + K_C over the slots described by field_slot[0..nb]
+// noff: r0(h)^(l + noff) in K_B; etable: expansion coefficients of K_C (see moment_plan_create)
 static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, const int* field_slot, int noff,
+                         int etable,
                          const double* dfactor, const double* dfactor_dev, double* clm, double* slm,
                          cudaStream_t st) {
   MomentPlan* mp = pl->mom;
@@ -1243,6 +1281,7 @@ static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, co
   q.ckpt = pl->ckpt;
   q.F = (const double*)(ws + lay.F);
   q.slot_r0 = (const double*)(ws + lay.slot_r0);
+  q.slot_q = (const double*)(ws + lay.slot_q);
   q.slot_ring = (const int*)(ws + lay.slot_ring);
   for (int i = 0; i <= nb; ++i) q.field_slot[i] = field_slot[i];
   q.G = (double*)(ws + lay.G);
@@ -1256,7 +1295,7 @@ static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, co
   f.nsplit = nsplit;
   f.nunits = mp->nunits;
   f.lb_unit0 = mp->lb_unit0;
-  f.E = mp->E + (noff == 4 ? (size_t)NMOMC * (pl->lmax + 1) : 0);
+  f.E = mp->E + (size_t)etable * NMOMC * (pl->lmax + 1);
   f.G = q.G;
   f.clm = clm;
   f.slm = slm;
@@ -1301,7 +1340,7 @@ int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const 
     MomSchedule* sc = nullptr;
     int rc = moment_atm_launch(pl, c, lay, ws, t0, nb, 0, pl->nlat, 0, &sc, st);
     if (rc != MHB200_OK) return rc;
-    rc = moment_reduce(pl, lay, ws, nb, sc->field_slot.data(), noff, dfactor, nullptr, clm + t0 * nout,
+    rc = moment_reduce(pl, lay, ws, nb, sc->field_slot.data(), noff, (noff == 2) ? 2 : 1, dfactor, nullptr, clm + t0 * nout,
                        slm + t0 * nout, st);
     if (rc != MHB200_OK) return rc;
   }
@@ -1344,8 +1383,9 @@ int moment_band_finish(mhb200_plan* pl, int nbands, int mode, int nslots, const 
                        double* slm, void* mom_ws, cudaStream_t st) {
   const MomWs lay = mom_layout(pl, (size_t)pl->nlat + (size_t)nbands * pl->mom->ncta_max, g_units_bound(pl, 1));
   const int field_slot[2] = {0, nslots};
-  return moment_reduce(pl, lay, (char*)mom_ws, 1, field_slot, (mode == MHB200_METHOD_BC05) ? 2 : 4, dfactor, nullptr,
-                       clm, slm, st);
+  const bool bc05 = (mode == MHB200_METHOD_BC05);
+  return moment_reduce(pl, lay, (char*)mom_ws, 1, field_slot, bc05 ? 2 : 4, bc05 ? 2 : 1, dfactor, nullptr, clm, slm,
+                       st);
 }
 
 bool moment_pressure_eligible(const mhb200_plan* pl, const double* plm_table) {
@@ -1389,6 +1429,7 @@ int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3],
     pp.trig = mp->trig;
     pp.F = (double*)(ws + lay.F);
     pp.slot_r0 = (double*)(ws + lay.slot_r0);
+    pp.slot_q = (double*)(ws + lay.slot_q);
     pp.slot_ring = (int*)(ws + lay.slot_ring);
     pp.flag = (int*)(ws + lay.flag);
     pp.rad_e = rad_e;
@@ -1404,7 +1445,7 @@ int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3],
     MHB_CUDA(cudaGetLastError());
     int field_slot[NB_SUB + 1];
     for (int i = 0; i <= nb; ++i) field_slot[i] = i * pl->nlat;
-    const int rc = moment_reduce(pl, lay, ws, nb, field_slot, 2, dfactor, dfactor_dev, clm + t0 * nout,
+    const int rc = moment_reduce(pl, lay, ws, nb, field_slot, 2, 0, dfactor, dfactor_dev, clm + t0 * nout,
                                  slm + t0 * nout, st);
     if (rc != MHB200_OK) return rc;
   }

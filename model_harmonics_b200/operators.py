@@ -8,6 +8,7 @@ as the reference does it, and hands device pointers to the C ABI (``include/mhb2
 Array operands may be NumPy arrays (copied to the device) or torch CUDA tensors (zero copy).
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -16,8 +17,9 @@ from . import _lib
 from . import _compat
 from .plan import get_plan, plm_table_for, require_device
 
-__all__ = ['gen_pressure_stokes', 'gen_atmosphere_stokes', 'gen_point_pressure',
-           'pressure_stokes_batch', 'atmosphere_stokes_batch', 'point_pressure_batch']
+__all__ = ['gen_pressure_stokes', 'gen_atmosphere_stokes', 'gen_point_pressure', 'gen_stokes',
+           'pressure_stokes_batch', 'atmosphere_stokes_batch', 'point_pressure_batch', 'stokes_batch',
+           'gen_point_pressure_tiles']
 
 
 def _stream_ptr():
@@ -161,6 +163,72 @@ def pressure_stokes_batch(P, G, R, lon, lat, LMAX=60, MMAX=None, WEIGHT=None, LO
     R_t, Rs = _grid_operand(R, device, nlat, nlon, True, 'R')
     clm, slm = _pressure_core(plan, P_t, P_t.stride(), G_t, Gs, R_t, Rs, P_t.shape[0],
                               factors.rad_e / 100.0, factors.mmwe, None)
+    return (clm.cpu().numpy(), slm.cpu().numpy()) if as_numpy else (clm, slm)
+
+
+# -----------------------------------------------------------------------------------------
+# radius-free sibling: gravity_toolkit.gen_stokes
+# -----------------------------------------------------------------------------------------
+def _stokes_prepare(lon, lat, LMAX, MMAX, UNITS, LOVE, WEIGHT, device):
+    LMAX = np.int64(LMAX)
+    MMAX = np.copy(LMAX) if (MMAX is None) else MMAX
+    lon, lat = np.squeeze(lon), np.squeeze(lat)
+    phi = lon * np.pi / 180.0
+    th = (90.0 - lat) * np.pi / 180.0
+    factors = _compat.units(lmax=LMAX).spatial(*LOVE)
+    int_fact = _weights(phi, th, WEIGHT)
+    if isinstance(UNITS, (list, tuple, np.ndarray)):
+        dfactor = np.array(UNITS, dtype=np.float64)              # custom degree-dependent factors
+    elif UNITS == 1:
+        dfactor = factors.cmwe                                   # cm w.e. (g/cm^2)
+    elif UNITS == 2:
+        dfactor = factors.cmwe                                   # Gt: cell masses, no area weighting
+        int_fact = np.full(len(th), 1.0e15 / (factors.rad_e**2))
+    elif UNITS == 3:
+        dfactor = factors.mmwe                                   # kg/m^2 (mm w.e.)
+    else:
+        raise ValueError('Unknown units %r' % (UNITS,))
+    plan = get_plan(phi, np.cos(th), int_fact, int(LMAX), int(MMAX), device)
+    return LMAX, MMAX, plan, np.asarray(dfactor, dtype=np.float64), len(th), len(phi)
+
+
+def gen_stokes(data, lon, lat, LMIN=0, LMAX=60, MMAX=None, UNITS=1, PLM=None, LOVE=None, WEIGHT=None):
+    """
+    Spherical harmonics of a gridded surface-mass field with no radial factor: the sibling operator the
+    2-D reanalysis driver and the SMB/TWS drivers call (``gravtk.gen_stokes``, reference call sites
+    ``reanalysis/reanalysis_monthly_harmonics.py:434``, ``TWS/gldas_monthly_harmonics.py:373``,
+    ``SMB/era5_smb_harmonics.py:248``).  It is ``gen_pressure_stokes`` with ``(R/rad_e)^(l+2)`` and the
+    gravity division removed, so it runs on the same kernels with R = rad_e = G = 1.  ``data`` may be
+    (lat, lon) or (lon, lat); ``UNITS``: 1 cm w.e., 2 Gt, 3 kg/m^2, or an array of degree factors;
+    ``WEIGHT`` (latitude integration weights) as the reanalysis driver passes it.
+    The third-party function is restated from its published algorithm (not vendored under /root/reference).
+    """
+    device = require_device()
+    LMAX, MMAX, plan, dfactor, nlat, nlon = _stokes_prepare(lon, lat, LMAX, MMAX, UNITS, LOVE, WEIGHT, device)
+    plm_tab = plm_table_for(plan, PLM, int(LMAX), int(MMAX))
+    lat_first = (np.shape(data)[0] == nlat)
+    P_t, Ps = _grid_operand(data, device, nlat, nlon, lat_first, 'data')
+    if P_t.dim() != 2:
+        raise ValueError('data must be a 2-D grid')
+    one = torch.ones(1, dtype=torch.float64, device='cuda:%d' % device)
+    clm, slm = _pressure_core(plan, P_t, Ps, one, (0, 0, 0), one, (0, 0, 0), 1, 1.0, dfactor, plm_tab)
+    clm, slm = clm[0].cpu().numpy(), slm[0].cpu().numpy()
+    if LMIN > 0:
+        clm[:int(LMIN), :] = 0.0
+        slm[:int(LMIN), :] = 0.0
+    return _make_harmonics(clm, slm, LMAX, MMAX)
+
+
+def stokes_batch(data, lon, lat, LMAX=60, MMAX=None, UNITS=1, LOVE=None, WEIGHT=None, as_numpy=True):
+    """Batched ``gen_stokes``: ``data`` is (T, nlat, nlon); returns (clm, slm) of shape (T, LMAX+1, MMAX+1)."""
+    device = require_device()
+    LMAX, MMAX, plan, dfactor, nlat, nlon = _stokes_prepare(lon, lat, LMAX, MMAX, UNITS, LOVE, WEIGHT, device)
+    P_t = _to_device(data, device)
+    if P_t.dim() != 3 or tuple(P_t.shape[1:]) != (nlat, nlon):
+        raise ValueError('data must be (T, nlat, nlon)')
+    one = torch.ones(1, dtype=torch.float64, device='cuda:%d' % device)
+    clm, slm = _pressure_core(plan, P_t, P_t.stride(), one, (0, 0, 0), one, (0, 0, 0), P_t.shape[0], 1.0, dfactor,
+                              None)
     return (clm.cpu().numpy(), slm.cpu().numpy()) if as_numpy else (clm, slm)
 
 
@@ -355,7 +423,8 @@ def atmosphere_stokes_batch(GPH, pressure, lon, lat, LMAX=60, MMAX=None, ELLIPSO
 # -----------------------------------------------------------------------------------------
 # scattered points
 # -----------------------------------------------------------------------------------------
-_point_ws = {}
+_point_ws = {}           # (device, CUDA stream handle) -> workspace tensor
+_point_ws_lock = threading.Lock()
 
 
 def _points_core(device, P_t, G_t, Gs, R_t, Rs, phi_t, theta_t, area_t, npts, nbatch, lmax, mmax, rad_e, dfactor):
@@ -364,10 +433,12 @@ def _points_core(device, P_t, G_t, Gs, R_t, Rs, phi_t, theta_t, area_t, npts, nb
     need = L.mhb200_points_workspace_bytes(int(npts), int(nbatch), int(lmax), int(mmax))
     if need == 0:
         raise ValueError('bad sizes for the point operator')
-    ws = _point_ws.get(device)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        _point_ws[device] = ws
+    key = (device, int(torch.cuda.current_stream().cuda_stream))
+    with _point_ws_lock:
+        ws = _point_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _point_ws[key] = ws
     clm = torch.empty((nbatch, lmax + 1, mmax + 1), dtype=torch.float64, device=dev)
     slm = torch.empty_like(clm)
     dfactor = np.ascontiguousarray(dfactor, dtype=np.float64)
@@ -445,3 +516,41 @@ def point_pressure_batch(P, G, R, lon, lat, AREA=None, LMAX=60, MMAX=None, LOVE=
     clm, slm = _points_core(device, P_t, G_t, Gs, R_t, Rs, phi_t, theta_t, area_t, npts, P_t.shape[0], int(LMAX),
                             int(MMAX), rad_e, dfactor)
     return (clm.cpu().numpy(), slm.cpu().numpy()) if as_numpy else (clm, slm)
+
+
+def gen_point_pressure_tiles(tiles, LMAX=60, MMAX=None, LOVE=None):
+    """
+    Sum over spatial tiles of ``gen_point_pressure`` -- the accumulation loop of the LLC-tile driver
+    (reference ``OBP/ecco_llc_tile_harmonics.py:235-260``: 13 calls whose harmonics are summed with
+    ``obp_Ylms.add``).  ``tiles`` is a sequence of ``(P, G, R, lon, lat, AREA)`` (NumPy or device arrays,
+    already reduced to the valid points of the tile).  The operator is linear in the points, so the tiles
+    are concatenated on the device and transformed by ONE kernel pass; nothing goes back to the host
+    between tiles.  ``P`` entries may carry a leading time axis (T, npts_k) for static-geometry batches:
+    the result is then a pair of (T, LMAX+1, MMAX+1) arrays instead of a harmonics object.
+    """
+    device = require_device()
+    dev = 'cuda:%d' % device
+    cols = [[], [], [], [], [], []]
+    batched = None
+    for tile in tiles:
+        P, G, R, lon, lat, AREA = tile
+        P_t = _to_device(P, device)
+        is_b = (P_t.dim() == 2)
+        batched = is_b if batched is None else batched
+        if is_b != batched:
+            raise ValueError('all tiles must be batched (T, npts) or all unbatched')
+        n = P_t.shape[-1] if is_b else P_t.numel()
+        cols[0].append(P_t if is_b else P_t.reshape(-1))
+        for k, a in ((1, G), (2, R), (3, lon), (4, lat), (5, AREA)):
+            t = _to_device(_flat(a), device).reshape(-1)
+            cols[k].append(t.expand(n) if t.numel() == 1 else t)
+            if cols[k][-1].numel() != n:
+                raise ValueError('tile operands must have one value per point (or a single value)')
+    if not cols[0]:
+        raise ValueError('no tiles')
+    P_all = torch.cat(cols[0], dim=-1)
+    G_all, R_all, lon_all, lat_all, A_all = (torch.cat(c) for c in cols[1:])
+    if batched:
+        return point_pressure_batch(P_all, G_all, R_all, lon_all, lat_all, AREA=A_all, LMAX=LMAX, MMAX=MMAX,
+                                    LOVE=LOVE)
+    return gen_point_pressure(P_all, G_all, R_all, lon_all, lat_all, AREA=A_all, LMAX=LMAX, MMAX=MMAX, LOVE=LOVE)

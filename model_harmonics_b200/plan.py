@@ -52,23 +52,33 @@ class GridPlan(object):
                    'mhb200_plan_create')
         self.handle = handle
         self.costh = costh
-        self._workspace = None
+        self._workspaces = {}     # CUDA stream handle -> workspace tensor
         self.tables = {}          # per-plan device tensors (atmosphere ring tables, PLM tables)
         self.lock = threading.Lock()
+
+    def _workspace_for_stream(self, need):
+        """
+        One workspace per (plan, CUDA stream): the kernels of a call keep partial sums and staged
+        operands there, so calls enqueued on different streams (two threads, or one thread switching
+        streams) must not share it (re-entrant per (device, stream)).  Same-stream calls
+        are ordered by the stream and reuse the buffer.
+        """
+        key = int(torch.cuda.current_stream().cuda_stream)
+        with self.lock:
+            ws = self._workspaces.get(key)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device='cuda:%d' % self.device)
+                self._workspaces[key] = ws
+        return ws
 
     def workspace(self, nbatch, nlev=0):
         need = _lib.lib().mhb200_grid_workspace_bytes(self.handle, int(nbatch), int(nlev))
         if need == 0:
             raise ValueError('bad batch size')
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device='cuda:%d' % self.device)
-        return self._workspace
+        return self._workspace_for_stream(need)
 
     def host_workspace(self, nbands):
-        need = _lib.lib().mhb200_host_workspace_bytes(self.handle, int(nbands))
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device='cuda:%d' % self.device)
-        return self._workspace
+        return self._workspace_for_stream(_lib.lib().mhb200_host_workspace_bytes(self.handle, int(nbands)))
 
     def close(self):
         if getattr(self, 'handle', None) is not None and self.handle.value:

@@ -171,3 +171,54 @@ def gen_point_pressure(P, G, R, lon, lat, AREA=None, LMAX=60, MMAX=None, LOVE=No
         Pm1[:] = np.copy(Pl)                                         # :153-154
         Pl[:] = np.copy(Pp1)
     return out
+
+
+def gen_stokes(data, lon, lat, LMIN=0, LMAX=60, MMAX=None, UNITS=1, PLM=None, LOVE=None, WEIGHT=None):
+    """
+    Restatement of the third-party ``gravity_toolkit.gen_stokes`` (pinned 1.2.7, not vendored under
+    /root/reference; call sites ``reanalysis/reanalysis_monthly_harmonics.py:434``,
+    ``TWS/gldas_monthly_harmonics.py:373``): cos/sin(m phi) dot products over longitude, then the
+    Legendre sum with ``plm * int_fact`` per degree and the degree-dependent unit factor.  PARITY
+    UNPINNED against the real package; pinned instead to ``gen_pressure_stokes`` above (itself pinned
+    to the reference), which it must equal for R = rad_e, G = 1, UNITS = 3
+    (``tests/test_oracle_vs_reference.py``).  ``WEIGHT`` is the keyword the reanalysis driver passes.
+    """
+    LMAX = np.int64(LMAX)
+    MMAX = np.copy(LMAX) if (MMAX is None) else MMAX
+    lon, lat = np.squeeze(lon), np.squeeze(lat)
+    nlat = len(lat)
+    phi = lon * np.pi / 180.0
+    th = (90.0 - lat) * np.pi / 180.0
+    if np.shape(data)[0] == nlat:
+        data = np.transpose(data)                                    # (lon, lat)
+    m = np.arange(MMAX + 1)
+    ccos = np.cos(np.dot(m[:, np.newaxis], phi[np.newaxis, :]))
+    ssin = np.sin(np.dot(m[:, np.newaxis], phi[np.newaxis, :]))
+    int_fact = _weights(phi, th, WEIGHT)
+    fac = units(lmax=LMAX).spatial(*LOVE)
+    if isinstance(UNITS, (list, tuple, np.ndarray)):
+        dfactor = np.array(UNITS, dtype=np.float64)
+    elif UNITS == 1:
+        dfactor = fac.cmwe
+    elif UNITS == 2:
+        dfactor = fac.cmwe
+        int_fact = np.full(nlat, 1.0e15 / (fac.rad_e**2))
+    elif UNITS == 3:
+        dfactor = fac.mmwe
+    else:
+        raise ValueError('Unknown units %r' % (UNITS,))
+    if PLM is None:
+        PLM, _ = plm_holmes(LMAX, np.cos(th))
+    plm = np.zeros((LMAX + 1, MMAX + 1, nlat))
+    for j in range(nlat):
+        plm[:, :, j] = PLM[:LMAX + 1, :MMAX + 1, j] * int_fact[j]
+    dcos = np.dot(ccos, data)
+    dsin = np.dot(ssin, data)
+    out = harmonics(lmax=LMAX, mmax=MMAX)
+    out.clm = np.zeros((LMAX + 1, MMAX + 1))
+    out.slm = np.zeros((LMAX + 1, MMAX + 1))
+    for l in range(int(LMIN), LMAX + 1):
+        mm = int(np.min([MMAX, l]))
+        out.clm[l, :mm + 1] = dfactor[l] * np.sum(plm[l, :mm + 1, :] * dcos[:mm + 1, :], axis=1)
+        out.slm[l, :mm + 1] = dfactor[l] * np.sum(plm[l, :mm + 1, :] * dsin[:mm + 1, :], axis=1)
+    return out

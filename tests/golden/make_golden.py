@@ -46,6 +46,25 @@ def hypsometric():
                         source='reference lines 349-383 executed by oracle/hypsometric_oracle.reference_loop')
 
 
+def driver_ops():
+    """tests/golden/driver_ops.npz: the drivers' own pre-step lines and tile loop executed on seeded inputs
+    (oracle/driver_ops_oracle.py reference_* functions; inputs rebuilt by tests/golden_cases.driver_case)."""
+    from oracle import driver_ops_oracle as oo
+    from oracle.gravtk_standin import harmonics
+    ref = ref_loader.load()
+    lon, lat, pressure, mean_p, ii, jj, dP, weight, tiles, L, LOVE = golden_cases.driver_case()
+    out = {}
+    for name, w in (('plain', None), ('weighted', weight)):
+        out['pressure_' + name] = np.stack([oo.reference_pressure_step(pressure, mean_p, t, lat, ii, jj, weight=w)
+                                            for t in range(pressure.shape[0])])
+        out['levels_' + name] = oo.reference_atmosphere_step(dP, lat, ii, jj, weight=w)
+    Y = oo.reference_tile_accumulation(*tiles, L, L, LOVE, ref.gen_point_pressure, harmonics)
+    out['tiles_clm'], out['tiles_slm'] = Y.clm, Y.slm
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'driver_ops.npz'),
+                        source='reference driver lines executed by oracle/driver_ops_oracle.py', **out)
+    print('driver_ops', {k: v.shape for k, v in out.items()})
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == '--big':
         # BASELINE-size cases (minutes of CPU each): all of them, or the ones named after --big
@@ -53,3 +72,4 @@ if __name__ == '__main__':
     else:
         main()
         hypsometric()
+        driver_ops()

@@ -165,3 +165,53 @@ def test_plm_table_differing_in_unsampled_entries_is_honoured():
     A = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, PLM=PLM, LOVE=LOVE)
     B = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, LOVE=LOVE)
     assert np.array_equal(A.clm, B.clm) and np.array_equal(A.slm, B.slm)
+
+
+def test_two_threads_two_streams_share_one_plan():
+    """SURVEY 8b re-entrancy: different fields in flight on two streams of one plan, from two threads."""
+    import threading
+    import torch
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 60
+    lon, lat = syn.grid_axes(181, 360)
+    LOVE = syn.love_numbers(L)
+    G, R = syn.surface_geometry(lon, lat, seed=60)
+    Gd, Rd = torch.from_numpy(G).cuda(), torch.from_numpy(R).cuda()
+    P = [torch.from_numpy(syn.pressure_fields(181, 360, 6, seed=61 + 10 * i)).cuda() for i in range(2)]
+    GPH, dP, geoid = syn.atmosphere_cube(20, 181, 360, seed=62)
+    cubes = [(torch.from_numpy(GPH * (1.0 + 0.01 * i)).cuda(), torch.from_numpy(dP * (1.0 - 0.02 * i)).cuda())
+             for i in range(2)]
+    ge = torch.from_numpy(geoid).cuda()
+    akw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE, as_numpy=False)
+
+    def work(i):
+        a = mh.pressure_stokes_batch(P[i], Gd, Rd, lon, lat, LMAX=L, LOVE=LOVE, as_numpy=False)
+        b = mh.atmosphere_stokes_batch(cubes[i][0][None], cubes[i][1][None], lon, lat, **akw)
+        return [x.clone() for x in a + b]
+
+    want = [work(0), work(1)]                      # single-threaded, default stream
+    torch.cuda.synchronize()
+    got = [None, None]
+    errors = []
+
+    def runner(i):
+        try:
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(25):                # many calls in flight on both streams at once
+                    got[i] = work(i)
+            stream.synchronize()
+        except Exception as exc:                   # surfaced in the main thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=runner, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(2):
+        for a, b in zip(got[i], want[i]):
+            assert torch.equal(a, b)               # fixed-order reductions: bit-identical to the serial run

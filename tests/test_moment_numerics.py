@@ -63,19 +63,25 @@ def test_truncation_bound_of_the_design_document():
 # Contracted-moment form (model_harmonics_b200/csrc/stokes_moments.cu): the binomial expansion is applied
 # AFTER the Fourier and Legendre sums, around a per-ring expansion point r0(h):
 #   C_lm = D_l sum_j C(l + n0, j) sum_h w_h P_lm(x_h) r0(h)^(l + n0) sum_p e^{i m phi_p} M_j[h, p]
+# (BC05 takes its moments in e = (r / r0)^2 - 1 with the generalised coefficients C((l + 2) / 2, j)).
 # Emulated here in NumPy, in the kernels' order of summation, against the oracle.
 # ---------------------------------------------------------------------------------------------------
-def _binom(nmom, L, off):
+def _binom(nmom, L, off, half=False):
+    """C(a, j), a = l + off, or the generalised C((l + off) / 2, j) of the expansion in e = (1 + d)^2 - 1."""
     E = np.zeros((nmom, L + 1))
     for l in range(L + 1):
-        for j in range(min(nmom, l + off + 1)):
-            E[j, l] = float(math.comb(l + off, j))
+        a = 0.5 * (l + off) if half else float(l + off)
+        c = 1.0
+        for j in range(nmom):
+            if j > 0:
+                c = c * (a - (j - 1)) / j
+            E[j, l] = c
     return E
 
 
-def _contract_moments(M, r0, w, PLM, eul, dfactor, L, off, scale):
+def _contract_moments(M, r0, w, PLM, eul, dfactor, L, off, scale, half=False):
     F = np.einsum('mp,jhp->hmj', eul, M)
-    E = _binom(M.shape[0], L, off)
+    E = _binom(M.shape[0], L, off, half)
     clm = np.zeros((L + 1, L + 1))
     slm = np.zeros((L + 1, L + 1))
     for l in range(L + 1):
@@ -111,8 +117,8 @@ def _atmosphere_emulation(GPH, dP, lon, lat, L, geoid, LOVE, method, hc=24000.0)
             H = z * (a1[:, None] + a2[:, None] * z)
             S = ((N[:, None] + geoid + H) * st[:, None])**2 + ((N[:, None] * (1 - ecc1**2) + geoid + H) * ct[:, None])**2
             q = dP[k] / (gs[:, None] + H * (g1[:, None] + g2[:, None] * H))
-            d = np.sqrt(S) / (rad_e * r0[:, None]) - 1.0
-            dmax = max(dmax, float(np.abs(d).max()))
+            d = S / (rad_e * r0[:, None])**2 - 1.0          # e = (r / r0)^2 - 1: no square root
+            dmax = max(dmax, 0.5 * float(np.abs(d).max()))
             t = q.copy()
             for j in range(NMOM):
                 M[j] += t
@@ -128,7 +134,7 @@ def _atmosphere_emulation(GPH, dP, lon, lat, L, geoid, LOVE, method, hc=24000.0)
                 M[j] += t
                 t = t * d
     eul = np.exp(1j * np.outer(np.arange(L + 1), phi))
-    return _contract_moments(M, r0, w, PLM, eul, dfactor, L, off, scale) + (dmax,)
+    return _contract_moments(M, r0, w, PLM, eul, dfactor, L, off, scale, half=(method == 'BC05')) + (dmax,)
 
 
 @pytest.mark.parametrize('method', ['BC05', 'SW02'])
