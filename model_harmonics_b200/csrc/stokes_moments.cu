@@ -694,7 +694,14 @@ struct LegParams {
   const int* flag;
 };
 
-__global__ void __launch_bounds__(128) legendre_moment_kernel(const __grid_constant__ LegParams q) {
+// Warp-specialised: warps 0-3 run the recursion (thread = slot of the current 128-slot block) and fill a
+// double-buffered 16-degree tile; warps 4-7 (row tile = warp - 4) contract it with the block's F fragments.
+// The dependent-chain recursion (latency bound) and the DMMA stream (pipe bound) overlap; hand-over by
+// named barriers (1, 2: buffer free; 3, 4: buffer full), 128 arrivals + 128 waits each.
+__device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, 256;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2) legendre_moment_kernel(const __grid_constant__ LegParams q) {
   if (*reinterpret_cast<const volatile int*>(q.flag) != 0) return;
   __shared__ double tile[2][32 * 64];
   const int unit = blockIdx.x, tt = blockIdx.y / q.nsplit, split = blockIdx.y % q.nsplit;
@@ -706,93 +713,134 @@ __global__ void __launch_bounds__(128) legendre_moment_kernel(const __grid_const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int first_sub = max(0, m - lbase) >> 4;      // 16-degree sub-blocks wholly below the diagonal are skipped
   const int nsub = ((lend - lbase) >> 4) + 1;
-  const bool from_ckpt = (q.ckpt != nullptr && lb > 0 && m <= lbase - 2);
-  const double* f1 = q.f1 + m;
-  const double* f2 = q.f2 + m;
-  const double pmm = q.pmm[m], sqm = q.sq[m];
+  const int nblocks = (s1 - s0 + 127) / 128;
+  const int total = nblocks * (nsub - first_sub);     // tiles handed over
 
-  double acc[8][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+  // Recursion multipliers of this (degree block, order) in shared memory, with seed rows that make the
+  // recursion uniform from its first degree: every row is  cur = (x a) p1 - b p2  (operation order of
+  // plm_holmes):  l = m: (0, -1) on the state (p2, p1) = (pmm, 0);  l = m + 1: (sqrt(2m + 3), 0);
+  // l >= m + 2: (f1, f2).
+  __shared__ double2 rec_tab[LBLK];
+  if (tid < LBLK) {
+    const int l = lbase + tid;
+    double2 r = make_double2(0.0, 0.0);
+    if (l == m) r = make_double2(0.0, -1.0);
+    else if (l == m + 1) r = make_double2(q.sq[m], 0.0);
+    else if (l > m + 1 && l <= lend) r = make_double2(q.f1[(size_t)l * q.Mpad + m], q.f2[(size_t)l * q.Mpad + m]);
+    rec_tab[tid] = r;
+  }
+  __syncthreads();
 
-  for (int sblk = s0; sblk < s1; sblk += 128) {
-    // A fragments of the block: F[slot][m][(cs, j)], row tile = warp
-    double af[32];
-#pragma unroll
-    for (int ks = 0; ks < 32; ++ks) {
-      const int s = sblk + 4 * ks + (lane & 3);
-      af[ks] = (s < s1) ? __ldg(q.F + ((size_t)s * q.Frows + m) * 32 + warp * 8 + (lane >> 2)) : 0.0;
-    }
-    const int s = sblk + tid;
-    const bool valid = (s < s1);
-    const int h = valid ? q.slot_ring[s] : 0;
-    const double rho = valid ? q.slot_r0[s] : 1.0;
-    const double qs = valid ? q.slot_q[s] : 0.0;
-    const double xv = q.x[h], wh = q.w[h];
-    const double rs = q.rescale[(size_t)h * q.Mpad + m];
-    // recursion state: (p2, p1) = values at degrees (l - 2, l - 1) for the next degree l
-    double p2 = 0.0, p1 = 0.0;
-    int lnext;                          // next degree the recursion produces
-    if (from_ckpt) {
-      const double* ck = q.ckpt + (((size_t)h * q.nlb + lb) * q.Mpad + m) * 2;
-      p2 = ck[0];
-      p1 = ck[1];
-      lnext = lbase;
-    } else {
-      lnext = m;                        // sectoral seed first (may lie one degree below the block)
-    }
-    auto step = [&]() -> double {        // produces degree lnext
-      double cur;
-      if (lnext == m) {
-        cur = pmm;
-      } else if (lnext == m + 1) {
-        cur = __dmul_rn(__dmul_rn(xv, sqm), p1);
+  if (warp < 4) {
+    // ---------------- producers: weighted P_lm(x_h) r0(h)^(l + noff) of 128 slots x 16 degrees per tile
+    const bool from_ckpt = (q.ckpt != nullptr && lb > 0 && m <= lbase - 2);
+    const double pmm = q.pmm[m];
+    const int ks = tid >> 2, k = tid & 3;
+    const int lstart = lbase + 16 * first_sub;      // first degree of the first tile
+    int it = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int s = s0 + blk * 128 + tid;
+      const bool valid = (s < s1);
+      const int h = valid ? q.slot_ring[s] : 0;
+      const double rho = valid ? q.slot_r0[s] : 1.0;
+      const double qs = valid ? q.slot_q[s] : 0.0;
+      const double xv = q.x[h];
+      // (P rs) wh of plm_holmes + weighting, folded into one factor; zero for slots past the end
+      const double sc = valid ? q.rescale[(size_t)h * q.Mpad + m] * q.w[h] : 0.0;
+      // recursion state (p2, p1) = values at the two degrees below the next one
+      double p2, p1;
+      if (from_ckpt) {
+        const double* ck = q.ckpt + (((size_t)h * q.nlb + lb) * q.Mpad + m) * 2;
+        p2 = ck[0];
+        p1 = ck[1];
+      } else if (m >= lbase) {
+        p2 = pmm;                          // the seed row of degree m produces pmm
+        p1 = 0.0;
       } else {
-        cur = __dsub_rn(__dmul_rn(__dmul_rn(xv, __ldg(f1 + (size_t)lnext * q.Mpad)), p1),
-                        __dmul_rn(__ldg(f2 + (size_t)lnext * q.Mpad), p2));
+        p2 = 0.0;                          // m = lbase - 1: the block starts at degree m + 1
+        p1 = pmm;
       }
-      p2 = p1;
-      p1 = cur;
-      ++lnext;
-      return cur;
-    };
-    while (lnext < lbase + 16 * first_sub && lnext < m + 2 && lnext <= lend) step();   // at most the seed degree
-#pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-      if (sub >= first_sub && sub < nsub) {
-        double* T = tile[sub & 1];
+      // A = sc r0^(l + noff), advanced by r0 per degree and restarted per tile from A0 (advanced by r0^16), so
+      // that no value is more than ~20 roundings away from an exact power; nq = (l + noff) q is the
+      // correction of the expansion point K_A really used (see residual3)
+      const double rho2 = rho * rho, rho4 = rho2 * rho2, rho8 = rho4 * rho4, rho16 = rho8 * rho8;
+      double A0 = sc * ipow(rho, lstart + q.noff);
+      for (int sub = first_sub; sub < nsub; ++sub, ++it) {
+        const int b = it & 1;
+        double* T = tile[b] + ks * 64 + k;
         const int l0 = lbase + 16 * sub;
-        double rp = ipow(rho, max(l0, m) + q.noff);
-        const int ks = tid >> 2, k = tid & 3;
+        double A = A0;
+        double nq = (double)(l0 + q.noff) * qs;
+        named_sync(1 + b);                 // consumers have released this buffer
 #pragma unroll
         for (int dl = 0; dl < 16; ++dl) {
           const int l = l0 + dl;
           double v = 0.0;
-          if (l >= m && l <= lend) {
-            const double cur = step();
-            // r0'^n = r0^n (1 - n q): the expansion point K_A really used (see residual3)
-            v = (__dmul_rn(__dmul_rn(cur, rs), wh) * rp) * fma(-(double)(l + q.noff), qs, 1.0);
-            rp *= rho;
+          if (l >= m && l <= lend) {       // uniform over the CTA
+            const double2 ab = rec_tab[l - lbase];
+            const double cur = __dsub_rn(__dmul_rn(__dmul_rn(xv, ab.x), p1), __dmul_rn(ab.y, p2));
+            p2 = p1;
+            p1 = cur;
+            v = cur * fma(-nq, A, A);
           }
-          T[ks * 64 + (dl >> 3) * 32 + ((((dl & 7) + ks) & 7) << 2) + k] = valid ? v : 0.0;
+          A *= rho;
+          nq += qs;
+          T[(dl >> 3) * 32 + ((((dl & 7) + ks) & 7) << 2)] = v;
         }
-        __syncthreads();
-        const double* Tb = T + (lane & 3);
-        const int n = lane >> 2;
+        named_arrive(3 + b);
+        A0 *= rho16;
+      }
+    }
+  } else {
+    // ---------------- consumers: acc[(cs, j) rows of this warp][degrees] += F^T (rows x slots) * tile
+    const int cw = warp - 4;
+    double acc[8][2];
 #pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const double b0 = Tb[kk * 64 + (((n + kk) & 7) << 2)];
-          const double b1 = Tb[kk * 64 + 32 + (((n + kk) & 7) << 2)];
-          dmma884(acc[2 * sub][0], acc[2 * sub][1], af[kk], b0);
-          dmma884(acc[2 * sub + 1][0], acc[2 * sub + 1][1], af[kk], b1);
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+    if (total >= 1) named_arrive(1);
+    if (total >= 2) named_arrive(2);
+    const int n = lane >> 2;
+    int it = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const int sblk = s0 + blk * 128;
+      // A fragments of the block: F[slot][m][(cs, j)], row tile = cw
+      double af[32];
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        const int s = sblk + 4 * kk + (lane & 3);
+        af[kk] = (s < s1) ? __ldg(q.F + ((size_t)s * q.Frows + m) * 32 + cw * 8 + (lane >> 2)) : 0.0;
+      }
+      // pull the next block's rows (256 bytes per slot) into L2 while this one is contracted
+      {
+        const int s = sblk + 128 + (tid - 128);
+        if (s < s1) {
+          const double* nx = q.F + ((size_t)s * q.Frows + m) * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
+        }
+      }
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        if (sub >= first_sub && sub < nsub) {
+          const int b = it & 1;
+          named_sync(3 + b);               // tile is full
+          const double* Tb = tile[b] + (lane & 3);
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) {
+            const double b0 = Tb[kk * 64 + (((n + kk) & 7) << 2)];
+            const double b1 = Tb[kk * 64 + 32 + (((n + kk) & 7) << 2)];
+            dmma884(acc[2 * sub][0], acc[2 * sub][1], af[kk], b0);
+            dmma884(acc[2 * sub + 1][0], acc[2 * sub + 1][1], af[kk], b1);
+          }
+          if (it + 2 < total) named_arrive(1 + b);     // the last two tiles have no successor
+          ++it;
         }
       }
     }
-    __syncthreads();
-  }
-  double* Gd = q.G + (((size_t)(tt * q.nsplit + split) * q.nunits + unit) * 4 + warp) * 512 + lane * 2;
+    double* Gd = q.G + (((size_t)(tt * q.nsplit + split) * q.nunits + unit) * 4 + cw) * 512 + lane * 2;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(Gd + nt * 64) = make_double2(acc[nt][0], acc[nt][1]);
+    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(Gd + nt * 64) = make_double2(acc[nt][0], acc[nt][1]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1286,7 +1334,7 @@ static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, co
   for (int i = 0; i <= nb; ++i) q.field_slot[i] = field_slot[i];
   q.G = (double*)(ws + lay.G);
   q.flag = (const int*)(ws + lay.flag);
-  legendre_moment_kernel<<<dim3(mp->nunits, nb * nsplit), 128, 0, st>>>(q);
+  legendre_moment_kernel<<<dim3(mp->nunits, nb * nsplit), 256, 0, st>>>(q);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());
   FinParams f;
