@@ -425,13 +425,16 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     // fold over the four symmetric columns (phi, -phi, pi - phi, pi + phi), held by the lanes sub = 0..3 of
     // this warp: lane sub = v ends up with fold variant v (0 even-order cosine, 1 even sine, 2 odd cosine,
     // 3 odd sine; see fold_chunk in stokes_grid.cu)
+    // (signs as exact +-1 multipliers of FMAs: one operation per stage instead of both branches and a select)
+    const double fs1 = (sub & 1) ? -1.0 : 1.0;                       // stage 1: y + fs1 x
+    const double fsx = (sub == 2) ? -1.0 : 1.0, fsz = (sub == 1) ? -1.0 : 1.0;     // stage 2: fsx x + fsz zz
 #pragma unroll
     for (int j = 0; j < NMOMC; ++j) {
       double x = acc[j];
       const double y = __shfl_xor_sync(0xffffffffu, x, 8);
-      x = (sub & 1) ? (y - x) : (x + y);
+      x = fma(fs1, x, y);
       const double zz = __shfl_xor_sync(0xffffffffu, x, 16);
-      acc[j] = (sub == 1) ? (x - zz) : (sub == 2) ? (zz - x) : (x + zz);
+      acc[j] = fma(fsz, zz, fsx * x);
     }
     // every warp has finished the previous chunk's contraction (reads of Mf)
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -514,56 +517,65 @@ struct PressMomParams {
   unsigned dbound_hi;
 };
 
+// Expansion point of every (field, ring): r0 = mid-range of R / rad_e over the ring, the correction q of the
+// point the moment kernel really uses (see residual3), and the slot's ring index.  grid (nlat, nbatch).
+__global__ void __launch_bounds__(256) ring_center_kernel(const __grid_constant__ PressMomParams p) {
+  __shared__ double red[2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.x, t = blockIdx.y;
+  const double* Rt = p.R + t * p.Rs[0] + h * p.Rs[1];
+  double lo = 1.0e300, hi = -1.0e300;
+  for (int col = tid; col < p.nlon; col += 256) {
+    const double v = __ldg(Rt + col * p.Rs[2]);
+    // a NaN radius must not be lost in the comparisons: it poisons both bounds (and then trips the guard)
+    lo = (v < lo || v != v) ? v : lo;
+    hi = (v > hi || v != v) ? v : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = (lo2 < lo || lo2 != lo2) ? lo2 : lo;
+    hi = (hi2 > hi || hi2 != hi2) ? hi2 : hi;
+  }
+  if (lane == 0) {
+    red[0][warp] = lo;
+    red[1][warp] = hi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      const double lo2 = red[0][w], hi2 = red[1][w];
+      lo = (lo2 < lo || lo2 != lo2) ? lo2 : lo;
+      hi = (hi2 > hi || hi2 != hi2) ? hi2 : hi;
+    }
+    const double r0 = (0.5 * (lo + hi)) * p.inv_rad;
+    const int slot = t * p.nlat + h;
+    p.slot_r0[slot] = r0;
+    p.slot_q[slot] = residual3(r0, p.rad_e, 1.0 / (p.rad_e * r0));     // r0 rad_e c = 1 + q
+    p.slot_ring[slot] = h;
+  }
+}
+
 __global__ void __launch_bounds__(256, 2) pressure_moment_kernel(const __grid_constant__ PressMomParams p) {
   extern __shared__ double psm[];
   double* Mf = psm;                              // [PNR][4 variants][PF_V]
-  double* red = Mf + PNR * PF_RING;              // [2][PNR][8 warps]
-  double* ringc = red + 2 * PNR * 8;             // [PNR] r0, [PNR] 1 / (rad_e r0)
+  double* ringc = Mf + PNR * PF_RING;            // [PNR] r0, [PNR] 1 / (rad_e r0)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mb = blockIdx.x % p.nmb, rg = blockIdx.x / p.nmb, t = blockIdx.y;
   const int hbase = rg * PNR;
 
-  // ---- expansion point of every ring of the group: mid-range of R over the ring
-  {
-    const double* Rt = p.R + t * p.Rs[0];
-#pragma unroll
-    for (int rr = 0; rr < PNR; ++rr) {
-      const int h = min(hbase + rr, p.nlat - 1);
-      double lo = 1.0e300, hi = -1.0e300;
-      for (int col = tid; col < p.nlon; col += 256) {
-        const double v = __ldg(Rt + h * p.Rs[1] + col * p.Rs[2]);
-        // a NaN radius must not be lost in the comparisons: it poisons both bounds
-        lo = (v < lo || v != v) ? v : lo;
-        hi = (v > hi || v != v) ? v : hi;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
-        lo = (lo2 < lo || lo2 != lo2) ? lo2 : lo;
-        hi = (hi2 > hi || hi2 != hi2) ? hi2 : hi;
-      }
-      if (lane == 0) {
-        red[rr * 8 + warp] = lo;
-        red[(PNR + rr) * 8 + warp] = hi;
-      }
-    }
-    __syncthreads();
-    if (tid < PNR) {
-      double lo = red[tid * 8], hi = red[(PNR + tid) * 8];
-      for (int w = 1; w < 8; ++w) {
-        const double lo2 = red[tid * 8 + w], hi2 = red[(PNR + tid) * 8 + w];
-        lo = (lo2 < lo || lo2 != lo2) ? lo2 : lo;
-        hi = (hi2 > hi || hi2 != hi2) ? hi2 : hi;
-      }
-      const double r0 = (0.5 * (lo + hi)) * p.inv_rad;
-      ringc[tid] = r0;
-      ringc[PNR + tid] = 1.0 / (p.rad_e * r0);
-    }
-    __syncthreads();
+  // expansion point of every ring of the group (ring_center_kernel): r0 and 1 / (rad_e r0)
+  if (tid < PNR) {
+    const int h = min(hbase + tid, p.nlat - 1);
+    const double r0 = p.slot_r0[t * p.nlat + h];
+    ringc[tid] = r0;
+    ringc[PNR + tid] = 1.0 / (p.rad_e * r0);
   }
+  __syncthreads();
 
   // produce-phase role: two passes over ring pairs; thread column (warp % 4, lane) of ring 2 pass + tid / 128
   const int sub = lane >> 3, jj = (warp & 3) * 8 + (lane & 7), rhalf = tid >> 7;
+  const double fs1 = (sub & 1) ? -1.0 : 1.0, fsx = (sub == 2) ? -1.0 : 1.0, fsz = (sub == 1) ? -1.0 : 1.0;
   // contraction role
   const int par = warp >> 2, gi = warp & 3;
   double facc[PNR][2][2][2];
@@ -620,9 +632,9 @@ __global__ void __launch_bounds__(256, 2) pressure_moment_kernel(const __grid_co
         // fold over the four symmetric columns (see atm_moment_kernel)
         double x = mj;
         const double y = __shfl_xor_sync(0xffffffffu, x, 8);
-        x = (sub & 1) ? (y - x) : (x + y);
+        x = fma(fs1, x, y);
         const double zz = __shfl_xor_sync(0xffffffffu, x, 16);
-        dst[(j >> 3) * 32 + (j & 7) * 4] = (sub == 1) ? (x - zz) : (sub == 2) ? (zz - x) : (x + zz);
+        dst[(j >> 3) * 32 + (j & 7) * 4] = fma(fsz, zz, fsx * x);
         mj *= d;
       }
     }
@@ -664,11 +676,6 @@ __global__ void __launch_bounds__(256, 2) pressure_moment_kernel(const __grid_co
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
           *reinterpret_cast<double2*>(Fs + cs * 16 + nt * 8) = make_double2(facc[rr][cs][nt][0], facc[rr][cs][nt][1]);
-      if (mb == 0 && tid == rr) {
-        p.slot_r0[slot] = ringc[rr];
-        p.slot_q[slot] = residual3(ringc[rr], p.rad_e, ringc[PNR + rr]);     // r0 rad_e c = 1 + q
-        p.slot_ring[slot] = h;
-      }
     }
   }
   if (__syncthreads_or(viol) && tid == 0) atomicOr(p.flag, 1);
@@ -859,10 +866,10 @@ struct FinParams {
 
 __global__ void __launch_bounds__(64) moment_finalize_kernel(const __grid_constant__ FinParams q) {
   if (*reinterpret_cast<const volatile int*>(q.flag) != 0) return;
-  const int l = blockIdx.x, tt = blockIdx.y;
+  const int l = blockIdx.x, tt = blockIdx.z;
   const double df = (q.dfactor_dev != nullptr) ? q.dfactor_dev[l] : q.dfactor[l];
   const int nt = (l & 63) >> 3, ll = (l & 7) >> 1, e = l & 1;
-  for (int m = threadIdx.x; m <= q.mmax; m += blockDim.x) {
+  for (int m = blockIdx.y * blockDim.x + threadIdx.x; m <= q.mmax; m += gridDim.y * blockDim.x) {
     double c = 0.0, s = 0.0;
     if (m <= l) {
       const int unit = q.lb_unit0[l >> 6] + m;
@@ -1351,7 +1358,7 @@ static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, co
   f.dfactor_dev = dfactor_dev;
   if (!dfactor_dev)
     for (int l = 0; l <= pl->lmax; ++l) f.dfactor[l] = dfactor[l];
-  moment_finalize_kernel<<<dim3(pl->lmax + 1, nb), 64, 0, st>>>(f);
+  moment_finalize_kernel<<<dim3(pl->lmax + 1, (pl->mmax + 64) / 64, nb), 64, 0, st>>>(f);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());
   return MHB200_OK;
@@ -1452,7 +1459,7 @@ int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3],
   MHB_CUDA(cudaMemsetAsync(ws + lay.flag, 0, sizeof(int), st));
   *flag_out = (const int*)(ws + lay.flag);
   const size_t nout = (size_t)(pl->lmax + 1) * (pl->mmax + 1);
-  const size_t smem = (size_t)(PNR * PF_RING + 2 * PNR * 8 + 2 * PNR) * sizeof(double);
+  const size_t smem = (size_t)(PNR * PF_RING + 2 * PNR) * sizeof(double);
   MHB_CUDA(cudaFuncSetAttribute(pressure_moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int t0 = 0; t0 < nbatch; t0 += nbmax) {
     const int nb = std::min(nbmax, nbatch - t0);
@@ -1486,6 +1493,8 @@ int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3],
     unsigned long long bits;
     memcpy(&bits, &bound, 8);
     pp.dbound_hi = (unsigned)(bits >> 32);
+    ring_center_kernel<<<dim3(pl->nlat, nb), 256, 0, st>>>(pp);
+    g_launches.fetch_add(1);
     profile_begin(st);
     pressure_moment_kernel<<<dim3(pp.ngroups * pp.nmb, nb), 256, smem, st>>>(pp);
     profile_end(st);
