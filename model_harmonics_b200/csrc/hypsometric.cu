@@ -28,8 +28,10 @@ struct HypParams {
   int nlev, nA, nAI;
   double R_dry, Pmin;
   float divisor;                       // outputs Z / divisor (float32 division), 1 = geopotential as is
+  float rdivisor;                      // float32(1 / divisor), correctly rounded
   double A[HYP_MAX_COEF], B[HYP_MAX_COEF], AI[HYP_MAX_COEF], BI[HYP_MAX_COEF];
   double C[HYP_MAX_COEF], LC[HYP_MAX_COEF];      // per level: estimate of Pnum / Pdom and its logarithm (log_ratio)
+  double poly[9];                                // 1/3, 1/5, ..., 1/19
 };
 
 // log(a / b) for a, b > 0, given a level-wide estimate c of the ratio and lc = log(c).
@@ -40,7 +42,10 @@ struct HypParams {
 // depends only weakly on the surface pressure, so with c taken at a reference surface pressure u stays at the
 // per-cent level; anything else (|u| > 0.1) takes log(a / b) as the reference writes it.  Both forms are
 // within an ulp of the exact value, which is all the float32 running sum can see.
-__device__ __forceinline__ double log_ratio(double a, double b, double c, double lc) {
+// (the series coefficients 1/3 ... 1/19 travel as kernel parameters so that the FMAs read them straight from
+// the constant bank; `u_out` lets the caller test |u| <= 0.1 once per level instead of branching per element)
+__device__ __forceinline__ double log_ratio_series(double a, double b, double c, double lc, const double* pc,
+                                                   double& u_out) {
   const double cb = c * b;
   const double num = a - cb, den = a + cb;
   double y;
@@ -50,17 +55,11 @@ __device__ __forceinline__ double log_ratio(double a, double b, double c, double
   double u = num * y;
   e = fma(-den, u, num);
   u = fma(e, y, u);
-  if (!(fabs(u) <= 0.1)) return log(__ddiv_rn(a, b));
+  u_out = u;
   const double u2 = u * u;
-  double pl = 1.0 / 19.0;
-  pl = fma(pl, u2, 1.0 / 17.0);
-  pl = fma(pl, u2, 1.0 / 15.0);
-  pl = fma(pl, u2, 1.0 / 13.0);
-  pl = fma(pl, u2, 1.0 / 11.0);
-  pl = fma(pl, u2, 1.0 / 9.0);
-  pl = fma(pl, u2, 1.0 / 7.0);
-  pl = fma(pl, u2, 1.0 / 5.0);
-  pl = fma(pl, u2, 1.0 / 3.0);
+  double pl = pc[8];
+#pragma unroll
+  for (int i = 7; i >= 0; --i) pl = fma(pl, u2, pc[i]);
   const double t = u + u;
   return lc + fma(t * u2, pl, t);
 }
@@ -99,27 +98,52 @@ __global__ void __launch_bounds__(256) hypsometric_kernel(const __grid_constant_
       tn = ld(Tp + (size_t)(k + 1) * stride);
       qn = ld(Qp + (size_t)(k + 1) * stride);
     }
+    // past the last coefficient the denominators are the Pmin floor (:363-368, :377-382): with the pair
+    // (Pmin, 0) the same expression max(a + b sp, Pmin) yields it, with no per-element select
     const bool lastA = (k + 1 == q.nA), lastI = (k + 1 == q.nAI);
-    const double a1 = lastA ? 0.0 : q.A[k + 1], b1 = lastA ? 0.0 : q.B[k + 1];
-    const double ai1 = lastI ? 0.0 : q.AI[k + 1], bi1 = lastI ? 0.0 : q.BI[k + 1];
+    const double a1 = lastA ? q.Pmin : q.A[k + 1], b1 = lastA ? 0.0 : q.B[k + 1];
+    const double ai1 = lastI ? q.Pmin : q.AI[k + 1], bi1 = lastI ? 0.0 : q.BI[k + 1];
     const double ck = q.C[k], lck = q.LC[k];
+    double lg[V], Pdom[V], umax = 0.0;
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+      const double pnext = __dadd_rn(a1, __dmul_rn(b1, sp[c]));        // :362-368
+      Pdom[c] = fmax(pnext, q.Pmin);
+      double u;
+      lg[c] = log_ratio_series(pk[c], Pdom[c], ck, lck, q.poly, u);
+      umax = fmax(umax, fabs(u));
+      if (u != u) umax = 1.0;
+      pk[c] = pnext;
+    }
+    if (umax > 0.1) {
+      // ratio far from the level's estimate: the logarithm as the reference writes it
+      // (pk was advanced above: the numerator of this level is recomputed)
+#pragma unroll
+      for (int c = 0; c < V; ++c) {
+        const double pnum = __dadd_rn(q.A[k], __dmul_rn(q.B[k], sp[c]));
+        lg[c] = log(__ddiv_rn(pnum, Pdom[c]));
+      }
+    }
     Vec zo, dfo;
 #pragma unroll
     for (int c = 0; c < V; ++c) {
       // :360  Tv = (1.0 + 0.609133 * QV) * T   (float64 on the widened values)
       const double Tv = __dmul_rn(__dadd_rn(1.0, __dmul_rn(0.609133, (double)qv.v[c])), (double)tv.v[c]);
-      // :362-368
-      const double pnext = __dadd_rn(a1, __dmul_rn(b1, sp[c]));
-      const double Pdom = lastA ? q.Pmin : fmax(pnext, q.Pmin);
       // :371  gh += R_dry * Tv * log(Pnum / Pdom)
-      const double term = __dmul_rn(__dmul_rn(q.R_dry, Tv), log_ratio(pk[c], Pdom, ck, lck));
+      const double term = __dmul_rn(__dmul_rn(q.R_dry, Tv), lg[c]);
       gh[c] = __double2float_rn(__dadd_rn((double)gh[c], term));
-      zo.v[c] = scale ? __fdiv_rn(gh[c], q.divisor) : gh[c];                                     // :373
+      // :373 (and the float32 division by GRAVITY of reanalysis_atmospheric_harmonics.py:357): correctly
+      // rounded quotient by a constant from its correctly rounded reciprocal (Markstein): q0 = gh r,
+      // q = q0 + (gh - q0 d) r with the residual exact in the FMA
+      float zq = gh[c];
+      if (scale) {
+        const float q0 = gh[c] * q.rdivisor;
+        zq = fmaf(fmaf(-q0, q.divisor, gh[c]), q.rdivisor, q0);
+      }
+      zo.v[c] = zq;
       // :375-383
       const double pinext = __dadd_rn(ai1, __dmul_rn(bi1, sp[c]));
-      const double Pupper = lastI ? q.Pmin : fmax(pinext, q.Pmin);
-      dfo.v[c] = __double2float_rn(__dsub_rn(Pupper, pik[c]));
-      pk[c] = pnext;
+      dfo.v[c] = __double2float_rn(__dsub_rn(fmax(pinext, q.Pmin), pik[c]));
       pik[c] = pinext;
     }
     *reinterpret_cast<Vec*>(Zp + (size_t)k * stride) = zo;
@@ -158,12 +182,14 @@ extern "C" int mhb200_geopotential_levels_f32(int device, const float* T, const 
   q.R_dry = R_dry;
   q.Pmin = Pmin;
   q.divisor = divisor;
+  q.rdivisor = 1.0f / divisor;
   for (int i = 0; i < HYP_MAX_COEF; ++i) {
     q.A[i] = (i < nA) ? A[i] : 0.0;
     q.B[i] = (i < nA) ? B[i] : 0.0;
     q.AI[i] = (i < nAI) ? AI[i] : 0.0;
     q.BI[i] = (i < nAI) ? BI[i] : 0.0;
   }
+  for (int i = 0; i < 9; ++i) q.poly[i] = 1.0 / (double)(2 * i + 3);
   // level-wide estimate of the pressure ratio Pnum / Pdom (at a reference surface pressure) and its logarithm
   for (int k = 0; k < HYP_MAX_COEF; ++k) {
     double c = 1.0;
