@@ -241,14 +241,16 @@ __device__ __forceinline__ void moment_elements(const double (&z)[W], const doub
   }
 }
 
+// dmax_hi: running maximum of the high words of |d| (compared with the guard once per CTA; NaN and Inf have
+// the largest high words, so they trip it too)
 template <int MODE, int W>
 __device__ __forceinline__ void moment_levels(const double (&z)[W], const double (&dpv)[W], const ColumnC& c,
-                                              double (&acc)[NMOMC], unsigned bound_hi, int& viol) {
+                                              double (&acc)[NMOMC], unsigned& dmax_hi) {
   double w[W], d[W];
   moment_elements<MODE, W>(z, dpv, c, w, d);
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    viol |= ((unsigned)(__double2hiint(d[i]) & 0x7fffffff) > bound_hi) ? 1 : 0;
+    dmax_hi = max(dmax_hi, (unsigned)__double2hiint(d[i]) & 0x7fffffffu);
     accumulate16(acc, w[i], d[i]);
   }
 }
@@ -305,19 +307,20 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
 #pragma unroll
     for (int sb = 0; sb < 4; ++sb) {
       const int x0 = __ldg(bs + sb);
-      const int xa = x0 - (((x0 % BOXA) + BOXA) % BOXA);
+      const int xa = x0 & ~(BOXA - 1);                 // two's complement: floors negative starts too
       tma_load_4d(dst + sb * BOX_ELEMS, &tmZ, &full[s], xa, h, g * MLG, tf);
       tma_load_4d(dst + (4 + sb) * BOX_ELEMS, &tmP, &full[s], xa, h, g * MLG, tf);
     }
   };
   for (int n = 0; n < MSTAGES - 1; ++n) issue(n);
 
-  const int pos = (p.dir[sub] > 0) ? jj : (MKCF - 1 - jj);
+  int pos = (p.dir[sub] > 0) ? jj : (MKCF - 1 - jj);
+  asm volatile("" : "+r"(pos));                      // keep it in a register (not re-derived from the constant bank)
   const int par = warp >> 2, gi = warp & 3;          // contraction role: order parity and group of 16 orders
   double facc[2][2][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i) (&facc[0][0][0])[i] = 0.0;
-  int viol = 0;
+  unsigned dmax_hi = 0;
   int slot = p.slot_base + p.cta_slot[blockIdx.x];
   int item = 0;
 
@@ -327,8 +330,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     const int h = p.h0 + rem / nchunks, c = rem % nchunks;
     col = __ldg(p.col_grid + c * MKC + tid);
     geo = (col >= 0 && p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + col * p.geo_s1) : 0.0;
-    const int x0 = __ldg(p.box_start + c * 4 + sub);
-    shift = ((x0 % BOXA) + BOXA) % BOXA;          // columns between the aligned box start and the run
+    shift = __ldg(p.box_start + c * 4 + sub) & (BOXA - 1);     // columns between the aligned box start and the run
   };
   int col_next, shift_next;
   double geo_next;
@@ -339,7 +341,8 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     const int h = p.h0 + rem / nchunks, c = rem % nchunks;
     const bool active = (col_next >= 0);
     const double geo = geo_next;
-    const int bpos = shift_next + pos;
+    // this thread's element of level 0 inside a stage (bytes)
+    const unsigned boff = (unsigned)((sub * BOX_ELEMS + shift_next + pos) * (int)sizeof(Tin));
     double sg = 1.0, sp = 1.0;
     if (p.field_scale != nullptr) {
       sg = __ldg(p.field_scale + 2 * (p.t0 + t));
@@ -384,29 +387,33 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       issue(item + MSTAGES - 1);
       const int s = item % MSTAGES;
       mbar_wait(&full[s], (item / MSTAGES) & 1);
-      const Tin* zs = stages + (size_t)s * STAGE_ELEMS + sub * BOX_ELEMS + bpos;
-      const Tin* ps = zs + 4 * BOX_ELEMS;
-      const int nl = min(MLG, p.nlev - g * MLG);
-      double z[MLG], dpv[MLG];
+      const char* sbase = reinterpret_cast<const char*>(stages) + (size_t)s * STAGE_BYTES + boff;
+      const Tin* zs = reinterpret_cast<const Tin*>(sbase);
+      const Tin* ps = reinterpret_cast<const Tin*>(sbase + 4 * BOX_ELEMS * sizeof(Tin));
+      const int nl = p.nlev - g * MLG;
+      {
+        // (guarded loads + selects on purpose: an unconditional 8-load fast path for full groups measured 6 %
+        // slower on the same box -- profiles/README.md, round 2 -- the predicated form lets ptxas spread the
+        // loads through the arithmetic); the tail group (nlev % 4 levels) runs narrower instantiations: no
+        // padded work
+        double z[MLG], dpv[MLG];
 #pragma unroll
-      for (int k = 0; k < MLG; ++k) {
-        z[k] = (k < nl) ? (double)zs[k * BOXW] : 0.0;
-        dpv[k] = (k < nl) ? (double)ps[k * BOXW] : 0.0;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
-      if (active) {
-        if (nl == MLG) {
-          moment_levels<MODE, MLG>(z, dpv, cc, acc, p.dbound_hi, viol);
-        } else {
-          // tail group (nlev % 4 levels): no padded work
-          if (nl & 2) {
+        for (int k = 0; k < MLG; ++k) {
+          z[k] = (k < nl) ? (double)zs[k * BOXW] : 0.0;
+          dpv[k] = (k < nl) ? (double)ps[k * BOXW] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (active) {
+          if (nl >= MLG) {
+            moment_levels<MODE, MLG>(z, dpv, cc, acc, dmax_hi);
+          } else if (nl & 2) {
             const double z2[2] = {z[0], z[1]}, d2[2] = {dpv[0], dpv[1]};
-            moment_levels<MODE, 2>(z2, d2, cc, acc, p.dbound_hi, viol);
+            moment_levels<MODE, 2>(z2, d2, cc, acc, dmax_hi);
           }
-          if (nl & 1) {
+          if (nl < MLG && (nl & 1)) {
             const double z1[1] = {(nl & 2) ? z[2] : z[0]}, d1[1] = {(nl & 2) ? dpv[2] : dpv[0]};
-            moment_levels<MODE, 1>(z1, d1, cc, acc, p.dbound_hi, viol);
+            moment_levels<MODE, 1>(z1, d1, cc, acc, dmax_hi);
           }
         }
       }
@@ -487,7 +494,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       ++slot;
     }
   }
-  if (__syncthreads_or(viol) && tid == 0) atomicOr(p.flag, 1);
+  if (__syncthreads_or(dmax_hi > p.dbound_hi) && tid == 0) atomicOr(p.flag, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
