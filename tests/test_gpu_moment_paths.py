@@ -215,3 +215,74 @@ def test_two_threads_two_streams_share_one_plan():
     for i in range(2):
         for a, b in zip(got[i], want[i]):
             assert torch.equal(a, b)               # fixed-order reductions: bit-identical to the serial run
+
+
+@pytest.mark.parametrize('nlon,lon0,centred,moment', [
+    (8, 0.0, False, True), (12, -180.0, False, True), (64, 0.0, True, True), (132, -180.0, True, True),
+    (260, 0.0, False, True), (1440, -180.0, False, True),
+    # rotated by three steps: still symmetric, but the fold's base columns are no contiguous run -> direct kernels
+    (516, 3 * 360.0 / 516, False, False),
+    # arbitrary offset: no mirror symmetry at all -> direct kernels, unfolded
+    (96, 7.5, False, False)])
+def test_moment_path_on_other_regular_longitude_grids(nlon, lon0, centred, moment):
+    """Grids starting at -180, cell-centred grids (no self-paired columns), grids rotated by whole steps, tiny and
+    multi-chunk rings: fold pairing, TMA box starts (aligned below odd starts, negative starts) and the
+    dropped duplicate columns, through both grid operators against the oracle."""
+    import torch
+    from oracle import stokes_oracle
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    nlat, nlev, L = 9, 6, 20
+    step = 360.0 / nlon
+    lon = lon0 + (np.arange(nlon) + (0.5 if centred else 0.0)) * step
+    lat = np.linspace(80.0, -80.0, nlat)
+    GPH, dP, geoid = syn.atmosphere_cube(nlev, nlat, nlon, seed=nlon)
+    LOVE = syn.love_numbers(L)
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=geoid, LOVE=LOVE)
+    n0 = _launches()
+    c, s = mh.atmosphere_stokes_batch(torch.from_numpy(GPH).cuda()[None], torch.from_numpy(dP).cuda()[None], lon, lat,
+                                      **kw)
+    took_moment_path = (_launches() - n0 == 5)
+    O = stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
+    assert rel_to_max(c[0], s[0], O.clm, O.slm) <= TOL
+    assert took_moment_path == moment
+    G, R = syn.surface_geometry(np.mod(lon, 360.0), lat, seed=nlon)
+    P = syn.pressure_fields(nlat, nlon, 1, seed=nlon)[0]
+    Y = mh.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, MMAX=11, LOVE=LOVE)
+    O = stokes_oracle.gen_pressure_stokes(P, G, R, lon, lat, LMAX=L, MMAX=11, LOVE=LOVE)
+    assert rel_to_max(Y.clm, Y.slm, O.clm, O.slm) <= TOL
+
+
+def test_sub_batching_of_long_batches():
+    """More fields than one K_A launch takes (8): 11 distinct float32 cubes, 19 fields off a shared cube,
+    20 pressure fields at LMAX 100; every field against its own single call."""
+    import torch
+    from model_harmonics_b200 import testing as syn
+    mh = _mh()
+    L = 30
+    lon, lat = syn.grid_axes(19, 40)
+    LOVE = syn.love_numbers(L)
+    cubes = [syn.atmosphere_cube(9, 19, 40, seed=90 + t, dtype=np.float32) for t in range(11)]
+    GPH = np.stack([c[0] for c in cubes])
+    dP = np.stack([c[1] for c in cubes])
+    kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=cubes[0][2], LOVE=LOVE)
+    n0 = _launches()
+    clm, slm = mh.atmosphere_stokes_batch(torch.from_numpy(GPH).cuda(), torch.from_numpy(dP).cuda(), lon, lat, **kw)
+    assert _launches() - n0 == 2 * 3 + 2
+    for t in (0, 7, 8, 10):
+        c1, s1 = mh.atmosphere_stokes_batch(torch.from_numpy(GPH[t:t + 1]).cuda(), torch.from_numpy(dP[t:t + 1]).cuda(),
+                                            lon, lat, **kw)
+        assert rel_to_max(clm[t], slm[t], c1[0], s1[0]) <= 1e-14
+    scales = np.array([syn.atmosphere_field_scalars(t) for t in range(19)])
+    g64, d64 = GPH[0].astype(np.float64), dP[0].astype(np.float64)
+    clm, slm = mh.atmosphere_stokes_batch(g64, d64, lon, lat, field_scale=scales, **kw)
+    for t in (0, 8, 18):
+        Y = mh.gen_atmosphere_stokes(g64 * scales[t, 0], d64 * scales[t, 1], lon, lat, **kw)
+        assert rel_to_max(clm[t], slm[t], Y.clm, Y.slm) <= 1e-14
+    G, R = syn.surface_geometry(lon, lat, seed=91)
+    P = syn.pressure_fields(19, 40, 20, seed=92)
+    LV = syn.love_numbers(100)
+    clm, slm = mh.pressure_stokes_batch(P, G, R, lon, lat, LMAX=100, LOVE=LV)
+    for t in (0, 9, 19):
+        Y = mh.gen_pressure_stokes(P[t], G, R, lon, lat, LMAX=100, LOVE=LV)
+        assert rel_to_max(clm[t], slm[t], Y.clm, Y.slm) <= 1e-14
