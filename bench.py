@@ -227,12 +227,34 @@ def bind_to_gpu_numa_node(torch, local):
         props = torch.cuda.get_device_properties(local)
         bus = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
         node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
-        if node < 0:
-            return {'numa_node': None, 'note': 'no NUMA affinity reported for %s' % bus}
         cpus = set()
-        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
-            lo, _, hi = part.partition('-')
-            cpus.update(range(int(lo), int(hi or lo) + 1))
+
+        def parse_list(text):
+            out = set()
+            for part in text.strip().split(','):
+                lo, _, hi = part.partition('-')
+                out.update(range(int(lo), int(hi or lo) + 1))
+            return out
+
+        if node >= 0:
+            cpus = parse_list(open('/sys/devices/system/node/node%d/cpulist' % node).read())
+        else:
+            # containers often report -1 in sysfs: ask the driver (nvidia-smi topo -m, "CPU Affinity" column)
+            topo = subprocess.run(['nvidia-smi', 'topo', '-m'], capture_output=True, text=True, timeout=20).stdout
+            lines = [ln for ln in topo.splitlines() if ln.strip()]
+            header = [h.strip() for h in lines[0].replace('\x1b[4m', '').replace('\x1b[0m', '').split('\t')]
+            col = next((i for i, h in enumerate(header) if h.startswith('CPU Affinity')), None)
+            row = next((ln for ln in lines[1:] if ln.split('\t')[0].strip() == 'GPU%d' % local), None)
+            if col is None or row is None:
+                return {'numa_node': None, 'note': 'no NUMA affinity reported for %s' % bus}
+            # the header line starts with an empty cell above the row labels, so columns line up by index
+            cells = [c.strip() for c in row.split('\t')]
+            cpus = parse_list(cells[col])
+            ncol = next((i for i, h in enumerate(header) if h.startswith('NUMA Affinity')), None)
+            try:
+                node = int(cells[ncol]) if ncol is not None else None
+            except (ValueError, IndexError):
+                node = None
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)

@@ -43,10 +43,10 @@ constexpr int NMOMC = 16;                 // moments per column
 constexpr int MKCF = 64;                  // contraction columns per chunk
 constexpr int MKC = 4 * MKCF;             // thread columns per chunk (four fold sub-blocks)
 constexpr int MLG = 4;                    // levels per TMA stage
-constexpr int MSTAGES = 4;                // stages in flight per CTA
+constexpr int MSTAGES = 4;                // stages per CTA (3 measured 5 % slower; 5 do not fit twice per SM)
 constexpr int MF_KS = 68;                 // folded-moment buffer: doubles per k-step (2 n-tiles x 32, +4 pad)
 constexpr int MF_V = 16 * MF_KS + 8;      // ... per fold variant (+8: variants land on different banks)
-constexpr int NB_SUB = 8;                 // fields per K_A launch (bounds the F workspace)
+constexpr int NB_SUB = 32;                // most fields per K_A launch (see nb_sub: the F workspace stays <= 256 MB)
 constexpr int MAX_SPLIT = 8;              // ring splits of K_B
 constexpr int G_UNIT = 4 * 8 * 64;        // doubles K_B writes per (field, split, unit): 4 row tiles x 8 n-tiles
 constexpr double MOM_CENTER_HEIGHT = 24000.0;   // expansion point above the ellipsoid [m] (atmosphere)

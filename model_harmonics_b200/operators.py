@@ -450,6 +450,23 @@ def _points_core(device, P_t, G_t, Gs, R_t, Rs, phi_t, theta_t, area_t, npts, nb
     return clm, slm
 
 
+_angle_cache = []          # [(weakref(lon), lon._version, weakref(lat), lat._version, phi_t, theta_t)]
+
+
+def _cached_point_angles(lon, lat, device):
+    import weakref
+    with _point_ws_lock:
+        for rl, vl, ra, va, phi_t, theta_t in _angle_cache:
+            if rl() is lon and ra() is lat and vl == lon._version and va == lat._version:
+                return phi_t, theta_t
+    phi_t = (_to_device(lon, device).reshape(-1) * (np.pi / 180.0)).contiguous()               # :111-113
+    theta_t = ((90.0 - _to_device(lat, device).reshape(-1)) * (np.pi / 180.0)).contiguous()
+    with _point_ws_lock:
+        _angle_cache.insert(0, (weakref.ref(lon), lon._version, weakref.ref(lat), lat._version, phi_t, theta_t))
+        del _angle_cache[4:]
+    return phi_t, theta_t
+
+
 def _flat(a):
     if isinstance(a, torch.Tensor):
         return a.reshape(-1)
@@ -470,9 +487,9 @@ def _points_prepare(lon, lat, AREA, LMAX, MMAX, LOVE, device):
         MMAX = np.copy(LMAX)
     if isinstance(lon, torch.Tensor) and isinstance(lat, torch.Tensor):
         # device-resident coordinates: np.radians(x) is the single multiply x*(pi/180), formed here
-        # in fp64 on the device with the same constant
-        phi_t = _to_device(lon, device).reshape(-1) * (np.pi / 180.0)               # :111-113
-        theta_t = (90.0 - _to_device(lat, device).reshape(-1)) * (np.pi / 180.0)
+        # in fp64 on the device with the same constant; static point sets (the drivers' tiles) are
+        # converted once: the cache holds the very tensor objects and their in-place version counters
+        phi_t, theta_t = _cached_point_angles(lon, lat, device)
     else:
         phi_t = _to_device(np.radians(_flat(lon)), device)
         theta_t = _to_device(np.radians(90.0 - _flat(lat)), device)
