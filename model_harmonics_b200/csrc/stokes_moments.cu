@@ -89,6 +89,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
 // q = n / d and sqrt(a), W independent elements wide (statement by statement across the elements so that
 // the instruction stream carries the ILP): fp64 SFU seed, one Newton step, one residual correction --
 // correctly rounded in the geometry pass's ranges (bench_micro/newton_check.cu, profiles/r01_newton_check.jsonl)
+#ifdef KA_DIV5
 template <int W>
 __device__ __forceinline__ void div_t(const double (&n)[W], const double (&d)[W], double (&q)[W]) {
   double y[W], e[W];
@@ -105,6 +106,24 @@ __device__ __forceinline__ void div_t(const double (&n)[W], const double (&d)[W]
 #pragma unroll
   for (int i = 0; i < W; ++i) q[i] = fma(e[i], y[i], q[i]);
 }
+#else
+// n / d within an ulp in four operations after the seed y (relative error |e| <= 2^-20, e = 1 - d y exact to
+// rounding):  n / d = n y (1 + e + e^2 + O(e^3)),  e^3 < 2^-60
+template <int W>
+__device__ __forceinline__ void div_t(const double (&n)[W], const double (&d)[W], double (&q)[W]) {
+  double y[W], e[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(d[i]));
+#pragma unroll
+  for (int i = 0; i < W; ++i) e[i] = fma(-d[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < W; ++i) q[i] = n[i] * y[i];
+#pragma unroll
+  for (int i = 0; i < W; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < W; ++i) q[i] = fma(q[i], e[i], q[i]);
+}
+#endif
 template <int W>
 __device__ __forceinline__ void sqrt_t(const double (&a)[W], double (&g)[W]) {
   double h[W], r[W];
@@ -144,11 +163,10 @@ __device__ __forceinline__ double residual_sq(double a, double b, double c) {
   return (p - 1.0) + p_lo;
 }
 
-// m[j] += w d^j, j < 16:  7 products + 16 accumulates
+// m[j] += w d^j, j < 16:  6 products + 16 accumulates
 __device__ __forceinline__ void accumulate16(double (&m)[NMOMC], double w, double d) {
   const double d2 = d * d, d3 = d2 * d, d4 = d2 * d2;
-  const double v4 = w * d4, d8 = d4 * d4;
-  const double v8 = w * d8, v12 = v8 * d4;
+  const double v4 = w * d4, v8 = v4 * d4, v12 = v8 * d4;
   m[0] += w;
   m[1] = fma(w, d, m[1]);
   m[2] = fma(w, d2, m[2]);
@@ -197,7 +215,8 @@ struct AtmMomParams {
 
 struct ColumnC {
   // BC05: a1, a2 orthometric-height factors (field scale folded in), st, ct, g0..g2 normal gravity
-  // gam = g0 + H (g1 + g2 H), NG = N + geoid, NG1 = N (1 - e^2) + geoid, cinv = 1 / (rad_e r0)^2
+  // all lengths scaled by c = 1 / (rad_e r0) = cinv:  H' = z (a1 + a2 z) with a1, a2 scaled, NG = c (N + geoid),
+  // NG1 = -(c N e^2) cos(theta), gam = g0 + H' (g1 + g2 H') with g1, g2 rescaled to H' 
   // SW02: rad_e, sg, inv_r0, c0 = geoid / (rad_e r0) - 1
   double a1, a2, st, ct, g0, g1, g2, NG, NG1, cinv;
   double rad_e, sg, inv_r0, c0;
@@ -213,18 +232,20 @@ __device__ __forceinline__ void moment_elements(const double (&z)[W], const doub
     // BC05 expands in e = (R / (rad_e r0))^2 - 1 = 2 d + d^2 with the generalised binomial series
     // r^n = r0^n (1 + e)^(n/2) = r0^n sum_j C(n/2, j) e^j  (same convergence: (n/2) e ~ n d) -- R^2 is what
     // the geometry produces, so no square root is needed
-    double H[W], S[W], gam[W];
+    // With c = 1 / (rad_e r0) folded into the column constants (H' = c H, A' = c (N + geoid + H)):
+    //   e = (A' sin(theta))^2 + ((A' - c N e^2) cos(theta))^2 - 1     (7 operations with H')
+    // sin(theta), cos(theta) stay the table's own values; the scaled constants round per column, not per ring
+    double H[W], gam[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) H[i] = z[i] * fma(c.a2, z[i], c.a1);
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      const double As = (c.NG + H[i]) * c.st, Zz = (c.NG1 + H[i]) * c.ct;
-      S[i] = fma(Zz, Zz, As * As);
+      const double A = c.NG + H[i];
+      const double As = A * c.st, Zz = fma(A, c.ct, c.NG1);
+      d[i] = fma(Zz, Zz, fma(As, As, -1.0));
       gam[i] = fma(H[i], fma(c.g2, H[i], c.g1), c.g0);
     }
     div_t<W>(dpv, gam, w);
-#pragma unroll
-    for (int i = 0; i < W; ++i) d[i] = fma(S[i], c.cinv, -1.0);
   } else {
     double den[W], num[W], t[W];
 #pragma unroll
@@ -363,11 +384,18 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       cc.g2 = (3.0 * gs) * (p.inv_rad * p.inv_rad);
       const double ex = N * cc.st, ez = N1 * cc.ct;
       r0 = sqrt(fma(ez, ez, ex * ex)) * p.inv_rad + p.hc * p.inv_rad;
-      const double rr = p.rad_e * r0;
-      cc.cinv = 1.0 / (rr * rr);
-      qs = 0.5 * residual_sq(r0, p.rad_e, cc.cinv);     // (r0 rad_e)^2 cinv = 1 + q;  r0'^n = r0^n (1 + q)^(-n/2)
-      cc.NG = N + geo;
-      cc.NG1 = N1 + geo;
+      // all lengths are scaled by c = 1 / (rad_e r0) (see moment_elements); the expansion point really used
+      // is 1 / (rad_e c):  r0 rad_e c = 1 + q,  r0'^n = r0^n (1 + q)^(-n)
+      const double cs = 1.0 / (p.rad_e * r0);
+      cc.cinv = cs;
+      qs = residual3(r0, p.rad_e, cs);
+      const double rcs = p.rad_e * r0;                 // 1 / c
+      cc.a1 *= cs;
+      cc.a2 *= cs;
+      cc.g1 *= rcs;
+      cc.g2 *= rcs * rcs;
+      cc.NG = (N + geo) * cs;
+      cc.NG1 = -(((N - N1) * cs) * cc.ct);
       cc.rad_e = cc.sg = cc.inv_r0 = cc.c0 = 0.0;
     } else {
       r0 = 1.0 + p.hc * p.inv_rad;
