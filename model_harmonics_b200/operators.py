@@ -333,7 +333,9 @@ def _cube_pair(GPH, pressure, device):
     return g.contiguous(), d.contiguous()
 
 
-_HOST_BANDS = 8
+import os as _os
+# latitude bands of the host-cube pipeline (<= 16): 2/4/8/16 bands measured 83.1/83.0/80.9/80.6 fields/s at C3
+_HOST_BANDS = int(_os.environ.get('MHB200_HOST_BANDS', '4'))
 
 
 def _host_cube_pair(GPH, pressure):
@@ -383,7 +385,7 @@ def gen_atmosphere_stokes(GPH, pressure, lon, lat, LMAX=60, MMAX=None, ELLIPSOID
     LMAX, MMAX, plan, ring_t, lon_t, plm_tab, geoid_t, gstr, rad_e, dfactor = _atmosphere_prepare(
         shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGHT, PLM, LOVE, device)
     host = _host_cube_pair(GPH, pressure)
-    if host is not None and shape[1] >= 2 * _HOST_BANDS:
+    if host is not None and shape[1] >= 16:
         # host cubes: latitude-band pipeline (copy of band b+1 overlaps the kernel of band b)
         clm, slm = _atmosphere_host(plan, host[0], host[1], geoid_t, gstr, ring_t, lon_t, shape[0], method,
                                     rad_e, dfactor, plm_tab)
