@@ -207,6 +207,17 @@ int mhb200_fold_probe(int nlon, const double* phi, int nth, int* sets, int* unus
 int mhb200_moment_schedule_probe(int nb, int nrings, int nchunks, int max_ctas, int* cta_unit,
                                  int* cta_slot, int* field_slot, int buf_ctas, int* nslots_out);
 
+/*
+ * mhb200_moment_layout_probe: chunk layout of the contracted-moment atmosphere kernel for nf contraction
+ *   columns whose four fold sub-blocks are given in `sets` (4 ints per column, as mhb200_fold_probe returns
+ *   them at fold level 2).  Fills col_grid[nchunks * 256] (grid column of every thread column, -1 = inactive:
+ *   past the end, or a duplicate of a lower sub-block), box_start[nchunks * 4] (first longitude of every TMA
+ *   box before alignment) and dir[4] (+1 ascending, -1 descending runs); returns 1 when every sub-block of
+ *   every chunk is a contiguous run (the TMA feed applies), 0 when not, -1 on bad arguments.
+ */
+int mhb200_moment_layout_probe(int nf, const int* sets, int* col_grid, int* box_start, int* dir,
+                               int max_chunks);
+
 /* counters for bench.py: kernels launched by this library since load (all threads) */
 uint64_t mhb200_launch_count(void);
 

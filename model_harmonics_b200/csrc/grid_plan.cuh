@@ -44,6 +44,8 @@ int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3],
                         const long long Gs[3], const double* R, const long long Rs[3], int nbatch, double rad_e,
                         const double* dfactor, const double* dfactor_dev, double* clm, double* slm, void* mom_ws,
                         const int** flag_out, cudaStream_t st);
+bool moment_layout(int nf, const std::vector<int>* const sets[4], int dir[4], std::vector<int>& col_grid,
+                   std::vector<int>& box_start);
 int moment_schedule(int nb, int nrings, int nchunks, int max_ctas, std::vector<int>& cta_unit,
                     std::vector<int>& cta_slot, std::vector<int>& field_slot, int* nslots);
 }  // namespace mhb

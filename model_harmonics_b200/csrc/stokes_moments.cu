@@ -1094,20 +1094,19 @@ int moment_schedule(int nb, int nrings, int nchunks, int max_ctas, std::vector<i
   return ncta;
 }
 
-int moment_plan_create(mhb200_plan* pl, const double* phi) {
-  pl->mom = nullptr;
-  if (pl->fold != 2) return MHB200_OK;
-  MomentPlan* mp = new MomentPlan();
-  pl->mom = mp;
-  const int nf = (int)pl->colp.size();
-  mp->nf = nf;
-  mp->nchunks = (nf + MKCF - 1) / MKCF;
-  mp->ncta_max = 2 * pl->num_sms;
-  const std::vector<int>* sets[4] = {&pl->colp, &pl->colq, &pl->colp2, &pl->colq2};
-  // thread column (warp, lane) of chunk c: sub = lane / 8, contraction column j = 64 c + 8 warp + lane % 8.
-  // A grid column that appears in two sub-blocks of the same contraction column (phi = 0, pi, +-pi/2) is
-  // kept in the first and dropped from the others, so every trig entry has weight 1.
-  std::vector<int> col_grid((size_t)mp->nchunks * MKC, -1), box_start((size_t)mp->nchunks * 4, 0);
+// Pure host logic (CPU-tested through mhb200_moment_layout_probe): thread-column map and TMA box starts of
+// the atmosphere kernel's chunks for the four fold sub-blocks sets[0..3] (grid columns at phi, -phi, pi - phi,
+// pi + phi of every contraction column).
+//   thread column (warp, lane) of chunk c: sub = lane / 8, contraction column j = 64 c + 8 warp + lane % 8.
+//   A grid column that appears in two sub-blocks of the same contraction column (phi = 0, pi, +-pi/2) is kept
+//   in the first and dropped from the others, so every trig entry has weight 1.
+//   Returns whether every sub-block of every chunk is a contiguous longitude run (ascending or descending with
+//   the contraction column, the same direction in all chunks) -- the condition for the TMA feed.
+bool moment_layout(int nf, const std::vector<int>* const sets[4], int dir[4], std::vector<int>& col_grid,
+                   std::vector<int>& box_start) {
+  const int nchunks = (nf + MKCF - 1) / MKCF;
+  col_grid.assign((size_t)nchunks * MKC, -1);
+  box_start.assign((size_t)nchunks * 4, 0);
   auto column = [&](int sb, int j) -> int {
     if (j >= nf) return -1;
     const int col = (*sets[sb])[j];
@@ -1118,16 +1117,16 @@ int moment_plan_create(mhb200_plan* pl, const double* phi) {
   // direction of every sub-block's run (from the first two contraction columns that are both kept)
   bool ok = true;
   for (int sb = 0; sb < 4; ++sb) {
-    int dir = 0;
-    for (int j = 0; j + 1 < nf && dir == 0; ++j) {
+    int d = 0;
+    for (int j = 0; j + 1 < nf && d == 0; ++j) {
       const int a = column(sb, j), b = column(sb, j + 1);
-      if (a >= 0 && b >= 0) dir = b - a;
+      if (a >= 0 && b >= 0) d = b - a;
     }
-    if (dir == 0) dir = 1;                       // a single column
-    if (dir != 1 && dir != -1) ok = false;
-    mp->dir[sb] = (dir < 0) ? -1 : 1;
+    if (d == 0) d = 1;                       // a single column
+    if (d != 1 && d != -1) ok = false;
+    dir[sb] = (d < 0) ? -1 : 1;
   }
-  for (int c = 0; c < mp->nchunks; ++c)
+  for (int c = 0; c < nchunks; ++c)
     for (int sb = 0; sb < 4; ++sb) {
       bool have = false;
       int start = 0;
@@ -1136,7 +1135,7 @@ int moment_plan_create(mhb200_plan* pl, const double* phi) {
         const int warp = jj >> 3, lane = sb * 8 + (jj & 7);
         col_grid[(size_t)c * MKC + warp * 32 + lane] = col;
         if (col < 0) continue;
-        const int pos = (mp->dir[sb] > 0) ? jj : (MKCF - 1 - jj);
+        const int pos = (dir[sb] > 0) ? jj : (MKCF - 1 - jj);
         if (!have) {
           start = col - pos;
           have = true;
@@ -1146,6 +1145,28 @@ int moment_plan_create(mhb200_plan* pl, const double* phi) {
       }
       box_start[(size_t)c * 4 + sb] = have ? start : 0;
     }
+  return ok;
+}
+
+int moment_plan_create(mhb200_plan* pl, const double* phi) {
+  pl->mom = nullptr;
+  if (pl->fold != 2) return MHB200_OK;
+  MomentPlan* mp = new MomentPlan();
+  pl->mom = mp;
+  const int nf = (int)pl->colp.size();
+  mp->nf = nf;
+  mp->nchunks = (nf + MKCF - 1) / MKCF;
+  mp->ncta_max = 2 * pl->num_sms;
+  const std::vector<int>* sets[4] = {&pl->colp, &pl->colq, &pl->colp2, &pl->colq2};
+  std::vector<int> col_grid, box_start;
+  const bool ok = moment_layout(nf, sets, mp->dir, col_grid, box_start);
+  auto column = [&](int sb, int j) -> int {
+    if (j >= nf) return -1;
+    const int col = (*sets[sb])[j];
+    for (int s2 = 0; s2 < sb; ++s2)
+      if ((*sets[s2])[j] == col) return -1;
+    return col;
+  };
   mp->tma_ok = ok;
   // pressure kernel: chunks of 32 contraction columns, thread column (warp % 4, lane)
   mp->nchunks32 = (nf + PKCF - 1) / PKCF;
@@ -1547,6 +1568,25 @@ int moment_pressure_run(mhb200_plan* pl, const double* P, const long long Ps[3],
 }  // namespace mhb
 
 extern "C" {
+// CPU-testable probe of the atmosphere kernel's chunk layout (no CUDA calls): sets holds 4 ints per contraction
+// column (grid columns at phi, -phi, pi - phi, pi + phi: the output of mhb200_fold_probe at fold level 2).
+// Fills col_grid[nchunks * 256] (-1 = inactive thread column), box_start[nchunks * 4], dir[4]; returns 1 when the
+// sub-blocks are contiguous runs (TMA feed possible), 0 when not, -1 on bad arguments.
+int mhb200_moment_layout_probe(int nf, const int* sets, int* col_grid, int* box_start, int* dir, int max_chunks) {
+  if (nf < 1 || !sets || !col_grid || !box_start || !dir) return -1;
+  const int nchunks = (nf + mhb::MKCF - 1) / mhb::MKCF;
+  if (nchunks > max_chunks) return -1;
+  std::vector<int> s4[4];
+  for (int i = 0; i < nf; ++i)
+    for (int k = 0; k < 4; ++k) s4[k].push_back(sets[4 * i + k]);
+  const std::vector<int>* ptr[4] = {&s4[0], &s4[1], &s4[2], &s4[3]};
+  std::vector<int> cg, bs;
+  const bool ok = mhb::moment_layout(nf, ptr, dir, cg, bs);
+  for (size_t i = 0; i < cg.size(); ++i) col_grid[i] = cg[i];
+  for (size_t i = 0; i < bs.size(); ++i) box_start[i] = bs[i];
+  return ok ? 1 : 0;
+}
+
 // CPU-testable probe of the moment path's static schedule (no CUDA calls): fills cta_unit[ncta + 1],
 // cta_slot[ncta], field_slot[nb + 1]; returns the number of CTAs (or -1), *nslots_out = slots.
 int mhb200_moment_schedule_probe(int nb, int nrings, int nchunks, int max_ctas, int* cta_unit, int* cta_slot,

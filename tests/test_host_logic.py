@@ -209,3 +209,59 @@ def test_standard_plm_table_matches_the_oracle_table_bitwise():
     mine = _compat.plm_table(30, 17, x)
     ref, _ = plm_holmes(30, x)
     assert np.array_equal(mine, ref[:, :18, :])
+
+
+@pytest.mark.parametrize('lon,tma', [
+    (np.arange(1440) * 0.25, True), (np.arange(360) * 1.0, True), (-180.0 + np.arange(120) * 3.0, True),
+    (np.arange(-179.5, 180.0, 1.0), True), (np.arange(8) * 45.0, True), (np.arange(260) * (360.0 / 260), True),
+    # rotated by three steps: both symmetries hold, but the fold's base columns are not one contiguous run
+    (3 * (360.0 / 516) + np.arange(516) * (360.0 / 516), False)])
+def test_moment_layout_probe_covers_every_column_once_with_aligned_runs(lon, tma):
+    """Chunk layout of the contracted-moment atmosphere kernel (csrc/stokes_moments.cu, moment_layout):
+    every grid column is owned by exactly one active thread column (duplicates of self-paired columns are
+    dropped), each fold sub-block of a chunk is one longitude run starting at box_start, and the kernel's
+    Fourier sums over the kept columns -- weight 1 everywhere -- reproduce the direct sums."""
+    phi, sets, fold, _, _ = _fold(lon, 256)
+    assert fold == 2
+    n, nf = len(phi), len(sets)
+    nchunks = (nf + 63) // 64
+    cg = np.zeros(nchunks * 256, dtype=np.int32)
+    bs = np.zeros(nchunks * 4, dtype=np.int32)
+    dr = np.zeros(4, dtype=np.int32)
+    rc = _lib.lib().mhb200_moment_layout_probe(nf, np.ascontiguousarray(sets.reshape(-1)).ctypes.data_as(INT_P),
+                                               cg.ctypes.data_as(INT_P), bs.ctypes.data_as(INT_P),
+                                               dr.ctypes.data_as(INT_P), nchunks)
+    assert rc == (1 if tma else 0)
+    cg = cg.reshape(nchunks, 8, 4, 8)              # [chunk][warp][sub][lane % 8]
+    owned = cg[cg >= 0]
+    assert len(owned) == n and len(set(owned.tolist())) == n          # every grid column exactly once
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal(n)
+    mmax = 30
+    dc, ds = np.zeros(mmax + 1), np.zeros(mmax + 1)
+    for c in range(nchunks):
+        for w in range(8):
+            for jo in range(8):
+                j = 64 * c + 8 * w + jo
+                if j >= nf:
+                    assert np.all(cg[c, w, :, jo] < 0)
+                    continue
+                x = [B[col] if col >= 0 else 0.0 for col in cg[c, w, :, jo]]
+                s12, d12, s34, d34 = x[0] + x[1], x[0] - x[1], x[2] + x[3], x[2] - x[3]
+                p = sets[j, 0]
+                assert cg[c, w, 0, jo] == p                             # sub-block 0 is never dropped
+                for m in range(mmax + 1):
+                    bc, bsn = (s12 + s34, d12 - d34) if m % 2 == 0 else (s12 - s34, d12 + d34)
+                    dc[m] += np.cos(m * phi[p]) * bc
+                    ds[m] += np.sin(m * phi[p]) * bsn
+                if tma:
+                    for sb in range(4):
+                        col = cg[c, w, sb, jo]
+                        if col >= 0:
+                            jj = 8 * w + jo
+                            pos = jj if dr[sb] > 0 else 63 - jj
+                            assert col == bs[4 * c + sb] + pos
+    m = np.arange(mmax + 1)[:, None]
+    want_c, want_s = np.cos(m * phi[None, :]) @ B, np.sin(m * phi[None, :]) @ B
+    scale = np.abs(want_c).max()
+    assert np.abs(dc - want_c).max() <= 1e-12 * scale and np.abs(ds - want_s).max() <= 1e-12 * scale
