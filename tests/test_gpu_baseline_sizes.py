@@ -36,6 +36,14 @@ def _literal(Y, gold):
     return float((np.abs(got - ref)[big] / np.abs(ref)[big]).max())
 
 
+def _per_degree(Y, gold):
+    """Informational: max over degrees of max_m |delta_lm| / amplitude_l(ref)."""
+    amp = np.sqrt((gold['clm']**2 + gold['slm']**2).sum(axis=1))
+    err = np.maximum(np.abs(Y.clm - gold['clm']), np.abs(Y.slm - gold['slm'])).max(axis=1)
+    ok = amp > 0
+    return float((err[ok] / amp[ok]).max())
+
+
 def test_c2_points_1e5_vs_reference_golden():
     import model_harmonics_b200 as mh
     func, args, kwargs = golden_cases.build_big('points_c2')
@@ -44,7 +52,8 @@ def test_c2_points_1e5_vs_reference_golden():
     Y = mh.gen_point_pressure(*args, **kwargs)
     assert_structure(Y.clm, Y.slm, 60, 60)
     e = rel_to_max(Y.clm, Y.slm, gold['clm'], gold['slm'])
-    print('C2 1e5 points: rel-to-max %.2e, literal per-coefficient (|ref| > 1e-3 max) %.2e' % (e, _literal(Y, gold)))
+    print('C2 1e5 points: rel-to-max %.2e, literal per-coefficient (|ref| > 1e-3 max) %.2e, per-degree %.2e'
+          % (e, _literal(Y, gold), _per_degree(Y, gold)))
     assert e <= TOL
 
 
@@ -65,7 +74,8 @@ def test_c3_full_field_vs_reference_golden(method, moments, monkeypatch):
     Y = mh.gen_atmosphere_stokes(g, d, args[2], args[3], **kwargs)
     assert_structure(Y.clm, Y.slm, 60, 60)
     e = rel_to_max(Y.clm, Y.slm, gold['clm'], gold['slm'])
-    print('C3 %s MHB200_MOMENTS=%s: rel-to-max %.2e, literal %.2e' % (method, moments, e, _literal(Y, gold)))
+    print('C3 %s MHB200_MOMENTS=%s: rel-to-max %.2e, per-degree (error / degree amplitude) %.2e'
+          % (method, moments, e, _per_degree(Y, gold)))
     assert e <= TOL
 
 
@@ -106,7 +116,7 @@ def test_c4_pressure_lmax360_vs_reference_golden():
     Y = mh.gen_pressure_stokes(*args, **kwargs)
     assert_structure(Y.clm, Y.slm, 360, 360)
     e = rel_to_max(Y.clm, Y.slm, gold['clm'], gold['slm'])
-    print('C4 721x1440 LMAX 360: rel-to-max %.2e, literal %.2e' % (e, _literal(Y, gold)))
+    print('C4 721x1440 LMAX 360: rel-to-max %.2e, literal %.2e, per-degree %.2e' % (e, _literal(Y, gold), _per_degree(Y, gold)))
     assert e <= TOL
 
 
