@@ -216,7 +216,8 @@ struct AtmMomParams {
 struct ColumnC {
   // BC05: a1, a2 orthometric-height factors (field scale folded in), st, ct, g0..g2 normal gravity
   // all lengths scaled by c = 1 / (rad_e r0) = cinv:  H' = z (a1 + a2 z) with a1, a2 scaled, NG = c (N + geoid),
-  // NG1 = -(c N e^2) cos(theta), gam = g0 + H' (g1 + g2 H') with g1, g2 rescaled to H' 
+  // st = lam = 2 cos(theta) K and ct = mu = K^2 - 1 with K = -(c N e^2) cos(theta) (see moment_elements),
+  // gam = g0 + H' (g1 + g2 H') with g1, g2 rescaled to H' 
   // SW02: rad_e, sg, inv_r0, c0 = geoid / (rad_e r0) - 1
   double a1, a2, st, ct, g0, g1, g2, NG, NG1, cinv;
   double rad_e, sg, inv_r0, c0;
@@ -232,17 +233,19 @@ __device__ __forceinline__ void moment_elements(const double (&z)[W], const doub
     // BC05 expands in e = (R / (rad_e r0))^2 - 1 = 2 d + d^2 with the generalised binomial series
     // r^n = r0^n (1 + e)^(n/2) = r0^n sum_j C(n/2, j) e^j  (same convergence: (n/2) e ~ n d) -- R^2 is what
     // the geometry produces, so no square root is needed
-    // With c = 1 / (rad_e r0) folded into the column constants (H' = c H, A' = c (N + geoid + H)):
-    //   e = (A' sin(theta))^2 + ((A' - c N e^2) cos(theta))^2 - 1     (7 operations with H')
-    // sin(theta), cos(theta) stay the table's own values; the scaled constants round per column, not per ring
+    // With c = 1 / (rad_e r0) folded into the column constants (H' = c H, A' = c (N + geoid + H)) and
+    // K = -c N e^2 cos(theta):
+    //   e = (A' sin)^2 + (A' cos + K)^2 - 1 = A'^2 (sin^2 + cos^2) + A' (2 cos K) + (K^2 - 1) = A' (A' + lam) + mu
+    // (5 operations with H').  sin^2 + cos^2 of the table's own values is 1 + O(1e-16), and mu rounds at 1e-16:
+    // both residuals are per-ring constants, computed exactly at the start of the unit and folded into the
+    // slot's correction q (see the caller), so nothing systematic is left at n * 1e-16.
     double H[W], gam[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) H[i] = z[i] * fma(c.a2, z[i], c.a1);
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       const double A = c.NG + H[i];
-      const double As = A * c.st, Zz = fma(A, c.ct, c.NG1);
-      d[i] = fma(Zz, Zz, fma(As, As, -1.0));
+      d[i] = fma(A, A + c.st, c.ct);
       gam[i] = fma(H[i], fma(c.g2, H[i], c.g1), c.g0);
     }
     div_t<W>(dpv, gam, w);
@@ -395,7 +398,23 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       cc.g1 *= rcs;
       cc.g2 *= rcs * rcs;
       cc.NG = (N + geo) * cs;
-      cc.NG1 = -(((N - N1) * cs) * cc.ct);
+      {
+        // e = A (A + lam) + mu takes sin^2 + cos^2 = 1 and a rounded mu: the exact residuals
+        //   dk = sin^2 + cos^2 - 1,  dm = (K^2 - 1) - mu   (error-free products and sums)
+        // shift e by (dk + dm) for the whole ring, i.e. multiply r^n by 1 + (n / 2)(dk + dm): folded into q
+        const double sn = cc.st, cn = cc.ct;
+        const double K = -(((N - N1) * cs) * cn);
+        const double p1 = sn * sn, e1 = fma(sn, sn, -p1), p2 = cn * cn, e2 = fma(cn, cn, -p2);
+        const double sm = p1 + p2, bb = sm - p1;
+        const double dk = ((sm - 1.0) + ((p1 - (sm - bb)) + (p2 - bb))) + (e1 + e2);
+        const double pk = K * K, ek = fma(K, K, -pk);
+        const double mu = pk - 1.0;
+        const double dm = (pk - (mu + 1.0)) + ek;
+        cc.st = (2.0 * cn) * K;        // lam
+        cc.ct = mu;
+        qs -= 0.5 * (dk + dm);
+      }
+      cc.NG1 = 0.0;
       cc.rad_e = cc.sg = cc.inv_r0 = cc.c0 = 0.0;
     } else {
       r0 = 1.0 + p.hc * p.inv_rad;
