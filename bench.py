@@ -56,8 +56,8 @@ def algorithmic_flops_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON, L=LMAX):
 
 def executed_flops_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON):
     """fp64 operations atm_moment_kernel issues per field: per (level, column) element
-    13 slots of geometry + 22 of moment accumulation, per column 512 FMA-slots of DMMA contraction."""
-    return 2 * nlat * nlon * (nlev * 35 + 512)
+    11 slots of geometry + 22 of moment accumulation, per column 512 FMA-slots of DMMA contraction."""
+    return 2 * nlat * nlon * (nlev * 33 + 512)
 
 
 def algorithmic_bytes_per_field(nlev=NLEV, nlat=NLAT, nlon=NLON, itemsize=8):
@@ -511,7 +511,7 @@ def run_cuda_arm(args):
                              'flops_per_launch': executed_flops_per_field() * T,
                              'achieved_tflops': executed_flops_per_field() * T / (ring_ms * 1e-3) / 1e12,
                              'frac': executed_flops_per_field() * T / (ring_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
-                             'note': 'fp64 operations the kernel issues (35 FMA-slots per level element + 512 per '
+                             'note': 'fp64 operations the kernel issues (33 FMA-slots per level element + 512 per '
                                      'column in the DMMA contraction, FMA = 2 flops)'},
                          'pipe_busy_pct_ncu': prof.get('pipe_fp64_plus_dmma_pct'),
                          'peak_source': 'fp64 DMMA m8n8k4 peak measured on this pool '

@@ -33,7 +33,8 @@ int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const 
                    const double* field_scale_dev, const double* geoid, long long geo_s0, long long geo_s1,
                    const double* ring_tab, int nlev, int nbatch, double rad_e, const double* dfactor,
                    double* clm, double* slm, void* mom_ws, const int** flag_out, cudaStream_t st);
-int moment_band_begin(mhb200_plan* pl, int nbands, void* mom_ws, const int** flag_out, cudaStream_t st);
+int moment_band_begin(mhb200_plan* pl, int nbands, int mode, const double* ring_tab, double rad_e, void* mom_ws,
+                      const int** flag_out, cudaStream_t st);
 int moment_band_launch(mhb200_plan* pl, int nbands, int mode, int dtype, const void* GPH, const void* dP,
                        const double* geoid, long long geo_s0, long long geo_s1, const double* ring_tab, int nlev,
                        double rad_e, int h0, int h1, int* slot_base, void* mom_ws, cudaStream_t st);

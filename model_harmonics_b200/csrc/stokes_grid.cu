@@ -1967,7 +1967,7 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* cpl, int dtype, const void*
   void* mom_ws = (char*)workspace + host_slots_bytes(pl, nbands);
   const int* mom_flag = nullptr;
   int mom_slots = 0;
-  if (mom && (rc = moment_band_begin(pl, nbands, mom_ws, &mom_flag, st)) != MHB200_OK) return rc;
+  if (mom && (rc = moment_band_begin(pl, nbands, method, ring_tab, rad_e, mom_ws, &mom_flag, st)) != MHB200_OK) return rc;
   for (int b = 0; b < nbands; ++b) {
     const int h0 = (int)((long long)pl->nlat * b / nbands), h1 = (int)((long long)pl->nlat * (b + 1) / nbands);
     // band copy: nlev rows of (h1-h0)*nlon elements, pitch = one (lat, lon) plane

@@ -200,6 +200,7 @@ struct AtmMomParams {
   const int* col_grid;         // [nchunks][256] grid column of thread column (warp, lane), -1 = inactive
   int dir[4];                  // +1: sub-block runs ascend with the contraction column, -1: descend
   const double* ring_tab;      // caller's 9 x nlat table (see mhb200.h)
+  const double* ringc;         // [nlat][RINGC] per-ring constants of the moment form (atm_ring_kernel)
   const double* geoid;
   long long geo_s0, geo_s1;
   const double* field_scale;   // device, 2 per field, or null
@@ -279,6 +280,52 @@ __device__ __forceinline__ void moment_levels(const double (&z)[W], const double
   }
 }
 
+// Per-ring constants of the BC05 moment form, one thread per ring (a few hundred operations that every thread
+// of atm_moment_kernel used to repeat for every work unit):
+//   [0] a1 c  [1] a2 c  [2] N  [3] c = 1 / (rad_e r0)  [4] lam  [5] mu  [6] g0  [7] g1 / c  [8] g2 / c^2
+//   [9] r0  [10] q   (see moment_elements and residual3)
+constexpr int RINGC = 12;
+__global__ void atm_ring_kernel(int nlat, const double* ring_tab, double rad_e, double hc, double* ringc) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nlat) return;
+  const double inv_rad = 1.0 / rad_e;
+  const double* rt = ring_tab + h;
+  const double a1 = rt[0], a2 = rt[nlat], N = rt[2 * nlat], N1 = rt[3 * nlat];
+  const double sn = rt[4 * nlat], cn = rt[5 * nlat], gs = rt[6 * nlat], c1 = rt[7 * nlat];
+  const double ex = N * sn, ez = N1 * cn;
+  // expansion point: the ellipsoid's radius at this latitude + hc, in units of rad_e
+  const double r0 = sqrt(fma(ez, ez, ex * ex)) * inv_rad + hc * inv_rad;
+  // all lengths are scaled by c = 1 / (rad_e r0); the expansion point really used is 1 / (rad_e c):
+  // r0 rad_e c = 1 + q,  r0'^n = r0^n (1 + q)^(-n)
+  const double cs = 1.0 / (rad_e * r0);
+  double qs = residual3(r0, rad_e, cs);
+  const double rcs = rad_e * r0;                 // 1 / c
+  // e = A (A + lam) + mu takes sin^2 + cos^2 = 1 and a rounded mu: the exact residuals
+  //   dk = sin^2 + cos^2 - 1,  dm = (K^2 - 1) - mu   (error-free products and sums)
+  // shift e by (dk + dm) for the whole ring, i.e. multiply r^n by 1 + (n / 2)(dk + dm): folded into q
+  const double K = -(((N - N1) * cs) * cn);
+  const double p1 = sn * sn, e1 = fma(sn, sn, -p1), p2 = cn * cn, e2 = fma(cn, cn, -p2);
+  const double sm = p1 + p2, bb = sm - p1;
+  const double dk = ((sm - 1.0) + ((p1 - (sm - bb)) + (p2 - bb))) + (e1 + e2);
+  const double pk = K * K, ek = fma(K, K, -pk);
+  const double mu = pk - 1.0;
+  const double dm = (pk - (mu + 1.0)) + ek;
+  qs -= 0.5 * (dk + dm);
+  double* o = ringc + (size_t)h * RINGC;
+  o[0] = a1 * cs;
+  o[1] = a2 * cs;
+  o[2] = N;
+  o[3] = cs;
+  o[4] = (2.0 * cn) * K;
+  o[5] = mu;
+  o[6] = gs;
+  o[7] = (-(gs * c1) * inv_rad) * rcs;
+  o[8] = ((3.0 * gs) * (inv_rad * inv_rad)) * (rcs * rcs);
+  o[9] = r0;
+  o[10] = qs;
+  o[11] = 0.0;
+}
+
 template <int MODE, typename Tin>
 __global__ void __launch_bounds__(256, 2)
 atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmP,
@@ -297,6 +344,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   double* Mf = reinterpret_cast<double*>(smraw + MSTAGES * STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(Mf + 4 * MF_V);
   uint64_t* empty = full + MSTAGES;
+  int* box_s = reinterpret_cast<int*>(empty + MSTAGES);      // [nchunks][4] copy of p.box_start
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane >> 3, jj = warp * 8 + (lane & 7);
@@ -309,6 +357,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < p.nchunks * 4; i += 256) box_s[i] = __ldg(p.box_start + i);
   __syncthreads();
 
   const int ngroups = p.ngroups, nchunks = p.nchunks;
@@ -317,23 +366,40 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   // Producer side of the pipeline: item n = (unit, level group) goes to stage n % MSTAGES.  The warp
   // n % 8 issues it (one lane), so the issue cost is spread over the CTA; before refilling a stage it
   // waits until all 8 warps have read the item that was there.
+  // The producer's position (field, ring, chunk, level group) of item n is carried incrementally by every
+  // thread (uniform, a handful of integer operations per stage) instead of being divided out by the issuing lane.
+  int pt, ph, pc, pg = 0;
+  {
+    const int t = u_begin / units_per_field, rem = u_begin - t * units_per_field;
+    pt = t;
+    ph = p.h0 + rem / nchunks;
+    pc = rem % nchunks;
+  }
   auto issue = [&](int n) {
-    if (n >= nitems || warp != (n & 7) || lane != 0) return;
-    const int s = n % MSTAGES, k = n / MSTAGES;
-    if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-    const int u = u_begin + n / ngroups, g = n % ngroups;
-    const int t = u / units_per_field, rem = u - t * units_per_field;
-    const int h = p.h0 + rem / nchunks, c = rem % nchunks;
-    const int tf = (p.fields_in_map > 1) ? t : 0;
-    mbar_expect_tx(&full[s], TX_BYTES);
-    Tin* dst = stages + (size_t)s * STAGE_ELEMS;
-    const int* bs = p.box_start + c * 4;
+    if (n < nitems && warp == (n & 7) && lane == 0) {
+      const int s = n % MSTAGES, k = n / MSTAGES;
+      if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
+      const int tf = (p.fields_in_map > 1) ? pt : 0;
+      mbar_expect_tx(&full[s], TX_BYTES);
+      Tin* dst = stages + (size_t)s * STAGE_ELEMS;
+      const int* bs = box_s + pc * 4;
 #pragma unroll
-    for (int sb = 0; sb < 4; ++sb) {
-      const int x0 = __ldg(bs + sb);
-      const int xa = x0 & ~(BOXA - 1);                 // two's complement: floors negative starts too
-      tma_load_4d(dst + sb * BOX_ELEMS, &tmZ, &full[s], xa, h, g * MLG, tf);
-      tma_load_4d(dst + (4 + sb) * BOX_ELEMS, &tmP, &full[s], xa, h, g * MLG, tf);
+      for (int sb = 0; sb < 4; ++sb) {
+        const int xa = bs[sb] & ~(BOXA - 1);             // two's complement: floors negative starts too
+        tma_load_4d(dst + sb * BOX_ELEMS, &tmZ, &full[s], xa, ph, pg * MLG, tf);
+        tma_load_4d(dst + (4 + sb) * BOX_ELEMS, &tmP, &full[s], xa, ph, pg * MLG, tf);
+      }
+    }
+    // advance to item n + 1
+    if (++pg == ngroups) {
+      pg = 0;
+      if (++pc == nchunks) {
+        pc = 0;
+        if (++ph == p.h0 + p.nrings) {
+          ph = p.h0;
+          ++pt;
+        }
+      }
     }
   };
   for (int n = 0; n < MSTAGES - 1; ++n) issue(n);
@@ -354,7 +420,7 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     const int h = p.h0 + rem / nchunks, c = rem % nchunks;
     col = __ldg(p.col_grid + c * MKC + tid);
     geo = (col >= 0 && p.geoid != nullptr) ? __ldg(p.geoid + h * p.geo_s0 + col * p.geo_s1) : 0.0;
-    shift = __ldg(p.box_start + c * 4 + sub) & (BOXA - 1);     // columns between the aligned box start and the run
+    shift = box_s[c * 4 + sub] & (BOXA - 1);     // columns between the aligned box start and the run
   };
   int col_next, shift_next;
   double geo_next;
@@ -375,45 +441,18 @@ atm_moment_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     ColumnC cc;
     double r0, qs;
     if (MODE == MHB200_METHOD_BC05) {
-      const double* rt = p.ring_tab + h;
-      const double N = __ldg(rt + 2 * p.nlat), N1 = __ldg(rt + 3 * p.nlat);
-      const double gs = __ldg(rt + 6 * p.nlat), c1 = __ldg(rt + 7 * p.nlat);
-      cc.a1 = __ldg(rt) * sg;
-      cc.a2 = __ldg(rt + p.nlat) * (sg * sg);
-      cc.st = __ldg(rt + 4 * p.nlat);
-      cc.ct = __ldg(rt + 5 * p.nlat);
-      cc.g0 = gs;
-      cc.g1 = -(gs * c1) * p.inv_rad;
-      cc.g2 = (3.0 * gs) * (p.inv_rad * p.inv_rad);
-      const double ex = N * cc.st, ez = N1 * cc.ct;
-      r0 = sqrt(fma(ez, ez, ex * ex)) * p.inv_rad + p.hc * p.inv_rad;
-      // all lengths are scaled by c = 1 / (rad_e r0) (see moment_elements); the expansion point really used
-      // is 1 / (rad_e c):  r0 rad_e c = 1 + q,  r0'^n = r0^n (1 + q)^(-n)
-      const double cs = 1.0 / (p.rad_e * r0);
-      cc.cinv = cs;
-      qs = residual3(r0, p.rad_e, cs);
-      const double rcs = p.rad_e * r0;                 // 1 / c
-      cc.a1 *= cs;
-      cc.a2 *= cs;
-      cc.g1 *= rcs;
-      cc.g2 *= rcs * rcs;
-      cc.NG = (N + geo) * cs;
-      {
-        // e = A (A + lam) + mu takes sin^2 + cos^2 = 1 and a rounded mu: the exact residuals
-        //   dk = sin^2 + cos^2 - 1,  dm = (K^2 - 1) - mu   (error-free products and sums)
-        // shift e by (dk + dm) for the whole ring, i.e. multiply r^n by 1 + (n / 2)(dk + dm): folded into q
-        const double sn = cc.st, cn = cc.ct;
-        const double K = -(((N - N1) * cs) * cn);
-        const double p1 = sn * sn, e1 = fma(sn, sn, -p1), p2 = cn * cn, e2 = fma(cn, cn, -p2);
-        const double sm = p1 + p2, bb = sm - p1;
-        const double dk = ((sm - 1.0) + ((p1 - (sm - bb)) + (p2 - bb))) + (e1 + e2);
-        const double pk = K * K, ek = fma(K, K, -pk);
-        const double mu = pk - 1.0;
-        const double dm = (pk - (mu + 1.0)) + ek;
-        cc.st = (2.0 * cn) * K;        // lam
-        cc.ct = mu;
-        qs -= 0.5 * (dk + dm);
-      }
+      const double* rc = p.ringc + (size_t)h * RINGC;
+      cc.a1 = __ldg(rc) * sg;
+      cc.a2 = __ldg(rc + 1) * (sg * sg);
+      cc.cinv = __ldg(rc + 3);
+      cc.NG = (__ldg(rc + 2) + geo) * cc.cinv;
+      cc.st = __ldg(rc + 4);           // lam
+      cc.ct = __ldg(rc + 5);           // mu
+      cc.g0 = __ldg(rc + 6);
+      cc.g1 = __ldg(rc + 7);
+      cc.g2 = __ldg(rc + 8);
+      r0 = __ldg(rc + 9);
+      qs = __ldg(rc + 10);
       cc.NG1 = 0.0;
       cc.rad_e = cc.sg = cc.inv_r0 = cc.c0 = 0.0;
     } else {
@@ -982,13 +1021,15 @@ size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 // layout of the moment region of a workspace
 struct MomWs {
-  size_t flag, slot_r0, slot_q, slot_ring, F, G, total;
+  size_t flag, ringc, slot_r0, slot_q, slot_ring, F, G, total;
 };
 MomWs mom_layout(const mhb200_plan* pl, size_t max_slots, size_t g_units) {
   MomWs w;
   size_t o = 0;
   w.flag = o;
   o += 256;
+  w.ringc = o;
+  o = align256(o + (size_t)pl->nlat * RINGC * sizeof(double));
   w.slot_r0 = o;
   o = align256(o + max_slots * sizeof(double));
   w.slot_q = o;
@@ -1304,7 +1345,8 @@ static int launch_atm_kernel(const MomCall& c, const CUtensorMap& tz, const CUte
                              int ncta, cudaStream_t st) {
   const size_t esz = (c.dtype == MHB200_F64) ? 8 : 4;
   const size_t box_bytes = ((MLG * (MKCF + 16 / esz) * esz + 127) / 128) * 128;
-  const size_t smem = (size_t)MSTAGES * 2 * 4 * box_bytes + 4 * MF_V * sizeof(double) + 2 * MSTAGES * 8;
+  const size_t smem = (size_t)MSTAGES * 2 * 4 * box_bytes + 4 * MF_V * sizeof(double) + 2 * MSTAGES * 8 +
+                      (size_t)ap.nchunks * 4 * sizeof(int);
 #define MHB_LAUNCH_ATM(MODE, T)                                                                              \
   do {                                                                                                       \
     auto kern = atm_moment_kernel<MODE, T>;                                                                  \
@@ -1360,6 +1402,7 @@ static int moment_atm_launch(mhb200_plan* pl, const MomCall& c, const MomWs& lay
   ap.col_grid = mp->col_grid;
   for (int i = 0; i < 4; ++i) ap.dir[i] = mp->dir[i];
   ap.ring_tab = c.ring_tab;
+  ap.ringc = (const double*)(ws + lay.ringc);
   ap.geoid = c.geoid;
   ap.geo_s0 = c.geo_s0;
   ap.geo_s1 = c.geo_s1;
@@ -1450,6 +1493,12 @@ int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const 
   char* ws = (char*)mom_ws;
   MHB_CUDA(cudaMemsetAsync(ws + lay.flag, 0, sizeof(int), st));
   *flag_out = (const int*)(ws + lay.flag);
+  if (mode == MHB200_METHOD_BC05) {
+    atm_ring_kernel<<<(pl->nlat + 127) / 128, 128, 0, st>>>(pl->nlat, ring_tab, rad_e, MOM_CENTER_HEIGHT,
+                                                            (double*)(ws + lay.ringc));
+    g_launches.fetch_add(1);
+    MHB_CUDA(cudaGetLastError());
+  }
   MomCall c;
   c.mode = mode;
   c.dtype = dtype;
@@ -1478,10 +1527,17 @@ int moment_atm_run(mhb200_plan* pl, int mode, int dtype, const void* GPH, const 
 }
 
 // Host-band path: one field, K_A per latitude band (as its H2D copy lands), one K_B/K_C at the end.
-int moment_band_begin(mhb200_plan* pl, int nbands, void* mom_ws, const int** flag_out, cudaStream_t st) {
+int moment_band_begin(mhb200_plan* pl, int nbands, int mode, const double* ring_tab, double rad_e, void* mom_ws,
+                      const int** flag_out, cudaStream_t st) {
   const MomWs lay = mom_layout(pl, (size_t)pl->nlat + (size_t)nbands * pl->mom->ncta_max, g_units_bound(pl, 1));
   MHB_CUDA(cudaMemsetAsync((char*)mom_ws + lay.flag, 0, sizeof(int), st));
   *flag_out = (const int*)((char*)mom_ws + lay.flag);
+  if (mode == MHB200_METHOD_BC05) {
+    atm_ring_kernel<<<(pl->nlat + 127) / 128, 128, 0, st>>>(pl->nlat, ring_tab, rad_e, MOM_CENTER_HEIGHT,
+                                                            (double*)((char*)mom_ws + lay.ringc));
+    g_launches.fetch_add(1);
+    MHB_CUDA(cudaGetLastError());
+  }
   return MHB200_OK;
 }
 

@@ -118,7 +118,7 @@ def test_moment_path_runs_three_kernels_plus_two_guarded_stubs():
     mh.atmosphere_stokes_batch(g[None], d[None], lon, lat, **kw)
     n0 = _launches()
     mh.atmosphere_stokes_batch(g[None], d[None], lon, lat, **kw)
-    assert _launches() - n0 == 5          # K_A, K_B, K_C + the direct ring / reduce kernels (exit at once)
+    assert _launches() - n0 == 6          # ring constants, K_A, K_B, K_C + the direct ring / reduce kernels (exit at once)
 
 
 def test_flipped_views_are_accepted_like_the_reference():
@@ -242,7 +242,7 @@ def test_moment_path_on_other_regular_longitude_grids(nlon, lon0, centred, momen
     n0 = _launches()
     c, s = mh.atmosphere_stokes_batch(torch.from_numpy(GPH).cuda()[None], torch.from_numpy(dP).cuda()[None], lon, lat,
                                       **kw)
-    took_moment_path = (_launches() - n0 == 5)
+    took_moment_path = (_launches() - n0 == 6)
     O = stokes_oracle.gen_atmosphere_stokes(GPH, dP, lon, lat, **kw)
     assert rel_to_max(c[0], s[0], O.clm, O.slm) <= TOL
     assert took_moment_path == moment
@@ -268,7 +268,7 @@ def test_sub_batching_of_long_batches():
     kw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=cubes[0][2], LOVE=LOVE)
     n0 = _launches()
     clm, slm = mh.atmosphere_stokes_batch(torch.from_numpy(GPH).cuda(), torch.from_numpy(dP).cuda(), lon, lat, **kw)
-    assert _launches() - n0 == 2 * 3 + 2
+    assert _launches() - n0 == 1 + 2 * 3 + 2
     for t in (0, 31, 32, 34):
         c1, s1 = mh.atmosphere_stokes_batch(torch.from_numpy(GPH[t:t + 1]).cuda(), torch.from_numpy(dP[t:t + 1]).cuda(),
                                             lon, lat, **kw)
