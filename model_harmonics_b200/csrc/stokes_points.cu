@@ -8,14 +8,14 @@
 //   C_lm + i S_lm = dfactor_l * sum_p W_l[p] * Plm(cos th_p) * e^{i m phi_p}
 //   W_l[p] = Pdisc_l(alpha_p) * (P_p/G_p) * (R_p/rad_e)^(l+2)
 //
-// Three kernels + a fixed-order reduce:
-//  (1) points_weights_kernel: one thread per point walks the degrees.  The disc factor
+// Two kernels + a fixed-order reduce (the two preparation roles share one launch, points_prepare_kernel):
+//  (1) weights role: one thread per point walks the degrees.  The disc factor
 //      Pdisc_l = (P_{l-1}(alpha) - P_{l+1}(alpha))/2 is a cancellation-prone 3-term recursion
 //      (error amplified by ~1/(1-alpha) ~ npts/2), so it is evaluated in EXACTLY the
 //      reference's operation order with round-to-nearest intrinsics and no FMA contraction
 //      (the degree-only quotients (2l+1)/(l+1), l/(l+1) come from a host table: IEEE division
 //      gives the same bits on both sides).
-//  (2) points_trig_kernel: the per (point, order) factors (u^m/1e-280) e^{i m phi}.
+//  (2) trig role: the per (point, order) factors (u^m/1e-280) e^{i m phi}, eight orders per thread.
 //  (3) points_contract_kernel: scatter-reduce.  A lane group of 4 lanes owns one pair of
 //      orders (m, mtop-m) -- pairing gives every group the same number of degree steps -- and
 //      each lane carries 8 points at a time through the Holmes-Featherstone recursion in
@@ -69,11 +69,52 @@ struct DegreeFactors {
   double v[DF_MAX];
 };
 
-// gen_point_pressure.py:126-147
-__global__ void points_weights_kernel(const PointParams q) {
+// One launch prepares both operands of the contraction; blockIdx.y selects the role.
+//   y <  nmg : per (point, order) factors for the orders [8 y, 8 y + 8)
+//              E[m][p] = (u_p^m / 1e-280) * (cos(m phi_p), sin(m phi_p)),  u = sqrt(1 - x^2) (0 -> eps)
+//              i.e. e^{i m phi} of gen_point_pressure.py:186-188 with the rescale of the scaled
+//              Holmes-Featherstone column folded in; cos(theta), u and the power u^(8 y) are formed once per
+//              thread and the power advanced by one multiplication per order
+//   y >= nmg : field t = y - nmg: W_l[p] of gen_point_pressure.py:126-147 (and, for t = 0, cos(theta) and u)
+constexpr int PT_MGROUP = 8;
+__global__ void points_prepare_kernel(const PointParams q, int nmg) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
   if (p >= q.npad) return;
+  if ((int)blockIdx.y < nmg) {
+    const int m0 = blockIdx.y * PT_MGROUP;
+    double u = 1.0, ph = 0.0, r = 0.0;
+    const bool live = (p < q.npts);
+    if (live) {
+      const double x = cos(q.theta[p]);
+      u = sqrt(1.0 - x * x);
+      if (u == 0.0) u = 2.220446049250313e-16;
+      ph = q.phi[p];
+      // u^m0 / 1e-280 (1 for the zonal order): restarted from a short power at every group of orders
+      r = (m0 == 0) ? 1.0 : 1.0e280;
+      double bb = u;
+      int k = m0;
+      while (k) {
+        if (k & 1) r *= bb;
+        bb *= bb;
+        k >>= 1;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PT_MGROUP; ++i) {
+      const int m = m0 + i;
+      if (m > q.mmax) break;
+      double2 e = make_double2(0.0, 0.0);
+      if (live) {
+        double sv, cv;
+        sincos((double)m * ph, &sv, &cv);
+        e = make_double2(r * cv, r * sv);
+        r = (m == 0) ? 1.0e280 * u : r * u;
+      }
+      q.E[(size_t)m * q.npad + p] = e;
+    }
+    return;
+  }
+  const int t = blockIdx.y - nmg;
   double* W = q.W + (size_t)t * (q.lmax + 1) * q.npad + p;
   if (p >= q.npts) {
     for (int l = 0; l <= q.lmax; ++l) W[(size_t)l * q.npad] = 0.0;
@@ -104,31 +145,6 @@ __global__ void points_weights_kernel(const PointParams q) {
     Pm1 = Pl;
     Pl = Pp1;
   }
-}
-
-// Per (point, order) factors of the contraction, one thread each:
-//   E[m][p] = (u_p^m / 1e-280) * (cos(m phi_p), sin(m phi_p)),  u = sqrt(1 - x^2) (0 -> eps)
-// i.e. e^{i m phi} of gen_point_pressure.py:186-188 with the rescale of the scaled
-// Holmes-Featherstone column folded in.  grid (npad/128, mmax+1); runs after the weights kernel
-// (which leaves u in ug).
-__global__ void points_trig_kernel(const PointParams q) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y;
-  if (p >= q.npad) return;
-  double2 e = make_double2(0.0, 0.0);
-  if (p < q.npts) {
-    double r = (m == 0) ? 1.0 : 1.0e280, bb = q.ug[p];
-    int k = m;
-    while (k) {
-      if (k & 1) r *= bb;
-      bb *= bb;
-      k >>= 1;
-    }
-    double sv, cv;
-    sincos((double)m * q.phi[p], &sv, &cv);
-    e = make_double2(r * cv, r * sv);
-  }
-  q.E[(size_t)m * q.npad + p] = e;
 }
 
 // grid: (ncta_p, n_mtiles, nbatch).  Fallback for degrees whose staged tables do not fit in shared
@@ -762,12 +778,9 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
   q.slm = slm_out;
 
   {
-    dim3 grid((unsigned)((y.npad + 127) / 128), nbatch);
-    points_weights_kernel<<<grid, 128, 0, st>>>(q);
-    g_launches.fetch_add(1);
-    MHB_CUDA(cudaGetLastError());
-    dim3 tgrid((unsigned)((y.npad + 127) / 128), mmax + 1);
-    points_trig_kernel<<<tgrid, 128, 0, st>>>(q);
+    const int nmg = (mmax + PT_MGROUP) / PT_MGROUP;
+    dim3 grid((unsigned)((y.npad + 127) / 128), nmg + nbatch);
+    points_prepare_kernel<<<grid, 128, 0, st>>>(q, nmg);
     g_launches.fetch_add(1);
     MHB_CUDA(cudaGetLastError());
   }
