@@ -151,6 +151,20 @@ int mhb200_atmosphere_stokes_host(const mhb200_plan* plan, int dtype,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same with the geoid as a contiguous (nlat, nlon) HOST grid (what a driver holds): it is staged through a
+ * plan-owned pinned buffer and copied behind the first band's cubes, so the staging of this pageable operand
+ * overlaps the DMA of the cubes instead of preceding the call.
+ */
+int mhb200_atmosphere_stokes_host_geoid(const mhb200_plan* plan, int dtype,
+                                        const void* GPH_host, const void* dP_host,
+                                        const double* geoid_host,
+                                        const double* ring_tab, const double* lon_tab,
+                                        int nlev, int nbands, int method, double rad_e,
+                                        const double* dfactor, const double* plm_table,
+                                        double* clm_host, double* slm_host,
+                                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * gen_point_pressure.py:126-154,160-194.  Scattered points with disc areas:
  *   C_lm + i S_lm = dfactor[l] * sum_p Pdisc_l(alpha_p) (P/G)_p (R_p/rad_e)^(l+2) Plm(cos th_p) e^{i m phi_p}
  * phi, theta, area are (npts) device arrays; P is (nbatch, npts); G and R are addressed

@@ -44,6 +44,10 @@ PROTOTYPES = {
                                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                                      _c_double_p, _vp, _c_double_p, _c_double_p, _vp,
                                                      ctypes.c_size_t, _vp]),
+    'mhb200_atmosphere_stokes_host_geoid': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _c_double_p, _vp, _vp,
+                                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                           _c_double_p, _vp, _c_double_p, _c_double_p, _vp,
+                                                           ctypes.c_size_t, _vp]),
     'mhb200_geopotential_levels_f32': (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _vp, _c_double_p, _c_double_p,
                                                       ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, ctypes.c_int,
                                                       ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_float,

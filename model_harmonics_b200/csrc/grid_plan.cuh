@@ -92,6 +92,7 @@ struct mhb200_plan {
   cudaEvent_t done_ev = nullptr;
   double* out_dev = nullptr;      // 2 x (lmax+1)(mmax+1)
   double* out_pinned = nullptr;
+  double *geo_dev = nullptr, *geo_pinned = nullptr;   // staging of a host geoid (mhb200_atmosphere_stokes_host_geoid)
   int* lb_first_tile_dev = nullptr;
   std::vector<int> lb_first_tile;
   std::mutex mu;

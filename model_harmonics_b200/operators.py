@@ -297,7 +297,8 @@ def _method_code(METHOD):
     raise ValueError("METHOD must be 'BC05' or 'SW02'")
 
 
-def _atmosphere_prepare(GPH_shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGHT, PLM, LOVE, device):
+def _atmosphere_prepare(GPH_shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGHT, PLM, LOVE, device,
+                        host_geoid_ok=False):
     LMAX = np.int64(LMAX)
     MMAX = np.copy(LMAX) if not MMAX else MMAX                       # :147-149
     nlat, nlon = GPH_shape[-2], GPH_shape[-1]
@@ -313,6 +314,11 @@ def _atmosphere_prepare(GPH_shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGH
     plm_tab = plm_table_for(plan, PLM, int(LMAX), int(MMAX))
     if GEOID is None:
         raise TypeError('GEOID is required (geoid height on the (lat, lon) grid, or a scalar)')
+    if host_geoid_ok and not isinstance(GEOID, torch.Tensor) and np.shape(GEOID) == (nlat, nlon):
+        # host-cube pipeline: the library stages the host geoid itself, behind the first band's cubes
+        gh = np.ma.getdata(GEOID) if isinstance(GEOID, np.ma.MaskedArray) else np.asarray(GEOID)
+        gh = np.ascontiguousarray(gh, dtype=np.float64)
+        return LMAX, MMAX, plan, ring_t, lon_t, plm_tab, gh, None, rad_e, dfactor
     geoid_t = _to_device(GEOID, device)
     if geoid_t.numel() == 1:
         geoid_t, gstr = geoid_t.reshape(1), (0, 0)
@@ -359,6 +365,17 @@ def _atmosphere_host(plan, g, d, geoid_t, geoid_strides, ring_t, lon_t, nlev, me
     ws = plan.host_workspace(_HOST_BANDS)
     dfactor = np.ascontiguousarray(dfactor, dtype=np.float64)
     dtype = _lib.F32 if g.dtype == np.float32 else _lib.F64
+    if geoid_strides is None:
+        # geoid_t is a contiguous host grid (see _atmosphere_prepare)
+        with plan.lock:
+            rc = L.mhb200_atmosphere_stokes_host_geoid(plan.handle, dtype, ctypes.c_void_p(g.ctypes.data),
+                                                       ctypes.c_void_p(d.ctypes.data), _lib.as_double_p(geoid_t),
+                                                       _ptr(ring_t), _ptr(lon_t), int(nlev), _HOST_BANDS, int(method),
+                                                       float(rad_e), _lib.as_double_p(dfactor), _ptr(plm_tab),
+                                                       _lib.as_double_p(clm), _lib.as_double_p(slm), _ptr(ws),
+                                                       ws.numel(), _stream_ptr())
+        _lib.check(rc, 'mhb200_atmosphere_stokes_host_geoid')
+        return clm, slm
     with plan.lock:
         rc = L.mhb200_atmosphere_stokes_host(plan.handle, dtype, ctypes.c_void_p(g.ctypes.data),
                                              ctypes.c_void_p(d.ctypes.data), _ptr(geoid_t),
@@ -382,10 +399,11 @@ def gen_atmosphere_stokes(GPH, pressure, lon, lat, LMAX=60, MMAX=None, ELLIPSOID
     shape = tuple(GPH.shape)
     if len(shape) != 3:
         raise ValueError('GPH must be (level, lat, lon)')
-    LMAX, MMAX, plan, ring_t, lon_t, plm_tab, geoid_t, gstr, rad_e, dfactor = _atmosphere_prepare(
-        shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGHT, PLM, LOVE, device)
     host = _host_cube_pair(GPH, pressure)
-    if host is not None and shape[1] >= 16:
+    use_host = host is not None and shape[1] >= 16
+    LMAX, MMAX, plan, ring_t, lon_t, plm_tab, geoid_t, gstr, rad_e, dfactor = _atmosphere_prepare(
+        shape, lon, lat, LMAX, MMAX, ELLIPSOID, GEOID, WEIGHT, PLM, LOVE, device, host_geoid_ok=use_host)
+    if use_host:
         # host cubes: latitude-band pipeline (copy of band b+1 overlaps the kernel of band b)
         clm, slm = _atmosphere_host(plan, host[0], host[1], geoid_t, gstr, ring_t, lon_t, shape[0], method,
                                     rad_e, dfactor, plm_tab)
