@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N="ncu --set full --import-source on --clock-control none"
+$N -k regex:points_fused -s 1 -c 1 -f -o gpurun_out/r2e_c2_p8 python bench_micro/prof_case.py c2 2 > gpurun_out/r2_ncu4.log 2>&1
+MHB200_POINTS_FUSED=6 $N -k regex:points_fused -s 1 -c 1 -f -o gpurun_out/r2e_c2_p6 python bench_micro/prof_case.py c2 2 >> gpurun_out/r2_ncu4.log 2>&1
+tail -3 gpurun_out/r2_ncu4.log

@@ -20,3 +20,17 @@ for a, b in ev:
 torch.cuda.synchronize()
 ms = sorted(a.elapsed_time(b) for a, b in ev)
 print('C2 ms median %.4f best %.4f  rel-to-max vs golden %.2e' % (ms[10], ms[0], err))
+# kernel-only times from the library's profile hook, if it is on
+try:
+    from model_harmonics_b200 import _lib
+    L = _lib.lib()
+    if hasattr(L, 'mhb200_profile_enable'):
+        pass
+except Exception:
+    pass
+# back-to-back stream of 20 calls
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(20): f()
+b.record(); torch.cuda.synchronize()
+print('C2 back-to-back ms per call %.4f' % (a.elapsed_time(b) / 20))

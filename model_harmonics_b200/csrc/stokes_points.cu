@@ -29,6 +29,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -61,6 +62,12 @@ struct PointParams {
   double* slots;                // [ncta_p][nbatch][2][lmax+1][mmax+1]
   int ncta_p;
   double *clm, *slm;
+  // fused kernel
+  const double* gl;             // [(lmax+1)][Mpad] multipliers of the one-multiplier recursion (points_fused_kernel)
+  const double* scale;          // [(lmax+1)][Mpad] its normalisation c_lm, applied by the reduce kernel (or null)
+  int tiles_per_cta, tiles_rem, fused_steps;   // CTA b takes tiles_per_cta (+1 if b < tiles_rem) consecutive tiles
+  int dbg;                      // timing experiments only (MHB200_POINTS_DBG): 1 skip the tile preparation after the
+                                // first tile, 2 skip the trig factors after the first tile, 4 skip the reduction
 };
 
 constexpr int DF_MAX = 448;      // degree factors travel as kernel parameters up to this many
@@ -546,6 +553,378 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_staged(const PointPa
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused variant (the default whenever two of its CTAs fit on an SM: LMAX up to ~74).  One launch reads the
+// six point arrays and writes the per-CTA partial sums; the weights W_l[p] and the factors u^m e^{i m phi}
+// never travel through HBM.
+//
+//  * Recursion with ONE multiplier.  With q_l = Plm / (u^m c_lm), c_lm = f2_lm c_(l-2)m, the
+//    Holmes-Featherstone step p_l = x f1 p_(l-1) - f2 p_(l-2) becomes q_l = (x g_lm) q_(l-1) - q_(l-2),
+//    g_lm = f1_lm c_(l-1)m / c_lm (host table, formed in extended precision): 5 fp64 operations per
+//    (point, l, m) instead of 6, and the normalisation c_lm leaves the point sum (points_reduce_kernel).
+//  * Two orders per lane at the same degree (a "duo" m, m+1), so one shared-memory read of W_l[p] serves two
+//    (point, l, m) elements: the round-1 kernel read 8 bytes per element and sat at ~90 % of the
+//    shared-memory bandwidth next to its arithmetic.
+//  * A warp = 4 duos (8 consecutive orders) x 8 lanes x 8 points per lane = one 64-point tile.  All lanes of
+//    a warp are at the SAME degree: the walk runs from the first order of the 8 to LMAX, an order m that
+//    starts d steps later idles through d steps with multiplier 0 (its state just rotates through
+//    0, +-1; those sums land in (l < m) entries that are never written out) and the state is seeded so
+//    that it arrives at (q_(m-1), q_m) = (0, 1) on time.  Warp w walks orders [8w, 8w+8) and then
+//    [8(7-w), 8(7-w)+8) of the CTA's 64-order tile: equal work for every warp, the change of orders is
+//    uniform across the warp (the e^{i m phi} factors of the second walk are computed there, with no
+//    divergence), and warps only meet at the tile boundaries.
+//  * The 8 lanes of a duo are combined every two steps by a transposed reduction (7 exchanges for 8 sums);
+//    each lane then owns one accumulator in shared memory.
+//  * Tile boundary: 64 threads walk the disc-weight recursion of one point each, in the reference's exact
+//    operation order (as points_prepare_kernel), straight into the shared-memory tile, with cos(theta), u
+//    and phi as three more rows.
+// ---------------------------------------------------------------------------------------
+constexpr int PF_NT = 128;       // 4 warps
+constexpr int PF_ORD = 64;       // orders per CTA (4 warps x 2 walks x 8 orders)
+constexpr int PF_AUX = 13;       // per-point rows next to the weights: x, phi, cos phi, sin phi, u, u^(m0 + 8k) k = 0..7
+
+// rows of one warp's accumulators / multipliers: both walks, each rounded up to an even number of steps
+__host__ __device__ inline int fused_walk_steps(int lmax, int mmax, int m0, int quad) {
+  const int mq = m0 + 8 * quad;
+  const int n = (mq <= mmax) ? (lmax + 1 - mq) : 0;
+  return (n + 1) & ~1;
+}
+
+template <int P>
+__device__ __forceinline__ void pf_load(const double* row, double (&v)[P]) {
+#pragma unroll
+  for (int k = 0; k < P / 2; ++k) {
+    const double2 a = *reinterpret_cast<const double2*>(row + 16 * k);
+    v[2 * k] = a.x;
+    v[2 * k + 1] = a.y;
+  }
+}
+
+// sin and cos of a (|a| < 2^19: Cody-Waite reduction with a three-part pi/2 whose leading parts have 33
+// bits, Taylor polynomials on [-pi/4, pi/4] whose truncation is < 3e-18; ~1 ulp).  ~25 fp64 operations and no
+// conversion instructions, against ~115 instructions for the general-purpose sincos().  The coefficients sit
+// in the constant bank, where the FMAs read them as operands.
+__constant__ double PF_SC[20] = {
+    0.6366197723675814, 6755399441055744.0, 1.5707963267341256, 6.077100506303966e-11, 2.0222662487959506e-21,
+    // sin: 1/3!, -1/5!, ... -1/17!  (of r - r z (c0 + z (c1 + ...)))
+    1.0 / 6.0, -1.0 / 120.0, 1.0 / 5040.0, -1.0 / 362880.0, 1.0 / 39916800.0, -1.0 / 6227020800.0,
+    1.0 / 1307674368000.0, -1.0 / 355687428096000.0,
+    // cos: -1/2!, 1/4!, ... 1/16!  (of 1 + z (c0 + z (c1 + ...)))
+    -0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0};
+__constant__ double PF_C16 = 1.0 / 20922789888000.0;
+
+__device__ __forceinline__ void pf_sincos(const double a, double& sn, double& cs) {
+  const double t = fma(a, PF_SC[0], PF_SC[1]);
+  const int n = __double2loint(t);
+  const double k = t - PF_SC[1];
+  double r = fma(-k, PF_SC[2], a);
+  r = fma(-k, PF_SC[3], r);
+  r = fma(-k, PF_SC[4], r);
+  const double z = r * r;
+  double ps = PF_SC[12];
+#pragma unroll
+  for (int i = 11; i >= 5; --i) ps = fma(ps, z, PF_SC[i]);
+  double pc = PF_C16;
+#pragma unroll
+  for (int i = 19; i >= 13; --i) pc = fma(pc, z, PF_SC[i]);
+  const double s0 = fma(-(z * r), ps, r);
+  const double c0 = fma(z, pc, 1.0);
+  // quadrant: n & 1 swaps, bit 1 of n (sin) / of n + 1 (cos) negates
+  const double sv = (n & 1) ? c0 : s0, cv = (n & 1) ? s0 : c0;
+  sn = (n & 2) ? -sv : sv;
+  cs = ((n + 1) & 2) ? -cv : cv;
+}
+
+template <int P>
+__global__ void __launch_bounds__(PF_NT, (P == 8) ? 2 : 3) points_fused_kernel(const PointParams q) {
+  constexpr int TILE = 8 * P;                        // points per tile: 8 lanes x P points
+  extern __shared__ __align__(16) double acc_s[];   // acc [4][NS][16] | dc [2][L+1] | tile [L+2+AUX][TILE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane >> 3, j = lane & 7;
+  const int t = blockIdx.z;
+  const int L = q.lmax;
+  const int m0 = blockIdx.y * PF_ORD;
+  const int NS = q.fused_steps;
+  double* acc_w = acc_s + (size_t)warp * NS * 16;
+  double* dc_s = acc_s + (size_t)4 * NS * 16;
+  double* tile = dc_s + 2 * ((L + 2) & ~1);
+  double* aux = tile + (size_t)(L + 2) * TILE;       // rows 0 .. L: weights, row L + 1: zeros
+  const int mqa = m0 + 8 * warp, mqb = m0 + 8 * (7 - warp);
+  const int nA = (mqa <= q.mmax) ? (L + 1 - mqa) : 0, nB = (mqb <= q.mmax) ? (L + 1 - mqb) : 0;
+  const int nA2 = (nA + 1) & ~1, nB2 = (nB + 1) & ~1;
+
+  for (int i = lane; i < NS * 16; i += 32) acc_w[i] = 0.0;
+  for (int i = tid; i <= L; i += PF_NT) {
+    dc_s[2 * i] = __ldg(q.dc1 + i);
+    dc_s[2 * i + 1] = __ldg(q.dc2 + i);
+  }
+  for (int i = tid; i < TILE; i += PF_NT) tile[(size_t)(L + 1) * TILE + i] = 0.0;   // the step past LMAX of an odd walk
+
+  const long long tile0 = (long long)blockIdx.x * q.tiles_per_cta + min((int)blockIdx.x, q.tiles_rem);
+  const long long tile1 = tile0 + q.tiles_per_cta + (((int)blockIdx.x < q.tiles_rem) ? 1 : 0);
+  // Roles inside a duo's 8 lanes (bits of j): b2 picks which of the two orders is the lane's slot A (the other is
+  // slot B), b1 which of cos / sin is the "first" component.  The lanes combine their sums by a transposed
+  // reduction in which every lane KEEPS its slot-A / first sums and SENDS its slot-B / second sums: the partner
+  // across b2 (b1) has the roles swapped, so no value has to be selected.  Only the last exchange (b0: which of
+  // the two steps) selects.  The lane ends up with: order ma + b2, component b1, step s + b0.
+  const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
+  double* acc_mine = acc_w + (b0 ? 16 : 0) + grp * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+  const int pcol = (tid & 63);                       // the point of the tile this thread prepares
+
+  for (long long tb = tile0; tb < tile1; ++tb) {
+    __syncthreads();       // every warp is done with the previous tile (first pass: tables are in place)
+    if (!((q.dbg & 1) && tb != tile0)) {
+      const long long p = tb * TILE + pcol;
+      const bool live = (pcol < TILE) && (p < q.npts);
+      if (tb + 1 < tile1 && pcol < TILE && p + TILE < q.npts) {
+        // the next tile's inputs towards L2 / L1 while this one is contracted
+        const long long pn = p + TILE;
+        if (tid < 64) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.area + pn));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.P + (size_t)t * q.npts + pn));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.G + pn * q.Gs));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.R + pn * q.Rs));
+        } else {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.theta + pn));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.phi + pn));
+        }
+      }
+      if (tid < 64) {
+        // warps 0, 1: the disc weights, gen_point_pressure.py:126-147 in the reference's operation order
+        // (see points_prepare_kernel)
+        if (pcol < TILE) {
+          double* col = tile + pcol;
+          if (live) {
+            const double alpha = __dsub_rn(1.0, __ddiv_rn(q.area[p], q.area_denom));
+            const double PG = __ddiv_rn(q.P[(size_t)t * q.npts + p], q.G[p * q.Gs]);
+            const double r = __ddiv_rn(q.R[p * q.Rs], q.rad_e);
+            double Pm1 = 1.0, Pl = 1.0;
+            double pw = __dmul_rn(r, r);
+            // blocks of four degrees: the loop-carried part (two dependent operations per degree) first, then the
+            // four independent tails, so that their latencies overlap
+            for (int l0 = 0; l0 <= L; l0 += 4) {
+              double pm[4], pp[4], pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const double2 c = *reinterpret_cast<const double2*>(dc_s + 2 * min(l0 + k, L));
+                const double Pp1 = __dsub_rn(__dmul_rn(__dmul_rn(c.x, alpha), Pl), __dmul_rn(c.y, Pm1));
+                pm[k] = Pm1;
+                pp[k] = Pp1;
+                pk[k] = pw;
+                pw = __dmul_rn(pw, r);
+                Pm1 = Pl;
+                Pl = Pp1;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const double Pdisc = __dmul_rn(__dsub_rn(pm[k], pp[k]), 0.5);
+                if (l0 + k <= L) col[(size_t)(l0 + k) * TILE] = __dmul_rn(__dmul_rn(Pdisc, PG), pk[k]);
+              }
+            }
+          } else {
+            for (int l = 0; l <= L; ++l) col[(size_t)l * TILE] = 0.0;
+          }
+        }
+      } else if (pcol < TILE) {
+        // warps 2, 3: the per-point rows
+        double* col = aux + pcol;
+        double x = 0.0, u = 1.0, ph = 0.0, cp = 1.0, sp = 0.0;
+        if (live) {
+          x = cos(q.theta[p]);
+          u = sqrt(1.0 - x * x);
+          if (u == 0.0) u = 2.220446049250313e-16;
+          ph = q.phi[p];
+          sincos(ph, &sp, &cp);
+        }
+        col[0 * TILE] = x;
+        col[1 * TILE] = ph;
+        col[2 * TILE] = cp;
+        col[3 * TILE] = sp;
+        col[4 * TILE] = u;
+        // u^(m0 + 8k), k = 0 .. 7
+        double pw = 1.0, bb = u;
+        for (int k = m0; k; k >>= 1) {
+          if (k & 1) pw *= bb;
+          bb *= bb;
+        }
+        const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          col[(5 + k) * TILE] = pw;
+          pw *= u8;
+        }
+      }
+    }
+    __syncthreads();
+
+    double x[P];
+    pf_load<P>(aux + 2 * j, x);
+
+    // one walk of this warp: orders [mq, mq + 8), degrees mq .. mq + n2 - 1, accumulator / multiplier rows from row0
+    auto walk = [&](const int mq, const int quad, const int n2, const int row0) {
+      if (n2 == 0) return;
+      const int ma = mq + 2 * grp;               // this lane's orders: ma, ma + 1
+      // slot A / B: first and second trig factor, recursion state
+      double fa[P], ga[P], fb[P], gb[P], pa1[P], pa2[P], pb1[P], pb2[P];
+      if ((q.dbg & 2) && tb != tile0) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          fa[i] = ga[i] = fb[i] = gb[i] = 0.5;
+          pa1[i] = pb2[i] = 0.0;
+          pa2[i] = pb1[i] = 1.0;
+        }
+      } else {
+        double ph[P], cp[P], sp[P], u[P], um[P];
+        pf_load<P>(aux + 1 * TILE + 2 * j, ph);
+        pf_load<P>(aux + 2 * TILE + 2 * j, cp);
+        pf_load<P>(aux + 3 * TILE + 2 * j, sp);
+        pf_load<P>(aux + 4 * TILE + 2 * j, u);
+        pf_load<P>(aux + (size_t)(5 + quad) * TILE + 2 * j, um);
+        const bool live_a = (ma <= q.mmax), live_b = (ma + 1 <= q.mmax);
+        // seeds: an order that starts d steps into the walk (d = 2 grp for ma, 2 grp + 1 for ma + 1) arrives at
+        // (q_(m-1), q_m) = (0, 1) on time
+        const double sgn = (grp & 1) ? 1.0 : -1.0;
+        const double dma = (double)ma, dmb = (double)(ma + 1);
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          // u^ma = u^mq u^(2 grp)
+          const double u2 = u[i] * u[i];
+          const double f = ((grp & 1) ? u2 : 1.0) * ((grp & 2) ? u2 * u2 : 1.0);
+          const double pwa = live_a ? um[i] * f : 0.0;
+          const double pwb = live_b ? pwa * u[i] : 0.0;
+          // gen_point_pressure.py:186-188: exp(1j * (m * phi)) of the ROUNDED product, for both orders.
+          // Order ma directly; order ma + 1 by one rotation: fl((ma+1) phi) = fl(ma phi) + phi + d with d formed
+          // exactly (both differences are exact), cos(a + phi + d) = cos(a + phi) - d sin(a + phi).
+          const double a = dma * ph[i], a2 = dmb * ph[i];
+          double sv, cv;
+          if (fabs(a2) < 500000.0) {
+            pf_sincos(a, sv, cv);
+          } else {
+            sincos(a, &sv, &cv);
+          }
+          const double d = (a2 - a) - ph[i];
+          const double c2 = fma(cv, cp[i], -(sv * sp[i])), s2 = fma(sv, cp[i], cv * sp[i]);
+          const double c0v = pwa * cv, s0v = pwa * sv;                           // order ma
+          const double c1v = pwb * fma(-d, s2, c2), s1v = pwb * fma(d, c2, s2);  // order ma + 1
+          const double cA = b2 ? c1v : c0v, sA = b2 ? s1v : s0v, cB = b2 ? c0v : c1v, sB = b2 ? s0v : s1v;
+          fa[i] = b1 ? sA : cA;
+          ga[i] = b1 ? cA : sA;
+          fb[i] = b1 ? sB : cB;
+          gb[i] = b1 ? cB : sB;
+          pa1[i] = b2 ? sgn : 0.0;
+          pa2[i] = b2 ? 0.0 : sgn;
+          pb1[i] = b2 ? 0.0 : sgn;
+          pb2[i] = b2 ? sgn : 0.0;
+        }
+      }
+      const double* wrow = tile + (size_t)mq * TILE + 2 * j;
+      // multipliers of this lane's two orders, one row of the table per degree (rows past LMAX and the
+      // entries with l <= m are zero, l = m + 1 is one): L1-resident, fetched one iteration ahead
+      const double* gpa = q.gl + (size_t)mq * q.Mpad + ma + (b2 ? 1 : 0);
+      const double* gpb = q.gl + (size_t)mq * q.Mpad + ma + (b2 ? 0 : 1);
+      const size_t gstride = (size_t)q.Mpad;
+      double ga0 = __ldg(gpa), gb0 = __ldg(gpb), ga1 = __ldg(gpa + gstride), gb1 = __ldg(gpb + gstride);
+      double* ap = acc_mine + (size_t)row0 * 16;
+      // one degree: v = {A first, A second, B first, B second}
+      auto step = [&](const double gA, const double gB, double (&v)[4]) {
+        double w[P];
+        pf_load<P>(wrow, w);
+        wrow += TILE;
+        double a1 = 0.0, a2 = 0.0, b1s = 0.0, b2s = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          const double qa = fma(x[i] * gA, pa1[i], -pa2[i]);
+          const double qb = fma(x[i] * gB, pb1[i], -pb2[i]);
+          pa2[i] = pa1[i];
+          pa1[i] = qa;
+          pb2[i] = pb1[i];
+          pb1[i] = qb;
+          const double ta = qa * w[i], tb2 = qb * w[i];
+          a1 = fma(ta, fa[i], a1);
+          a2 = fma(ta, ga[i], a2);
+          b1s = fma(tb2, fb[i], b1s);
+          b2s = fma(tb2, gb[i], b2s);
+        }
+        v[0] = a1; v[1] = a2; v[2] = b1s; v[3] = b2s;
+      };
+      // Transposed reduction over the duo's 8 lanes: keep slot A, receive the partner's slot B (4 exchanges), keep
+      // the first component, receive the partner's second (2), then the step (1).  With 8 points per lane there
+      // are registers to run it ONE ITERATION LATE, its exchanges placed between the two steps of the next
+      // iteration, so that the shuffle latencies overlap that arithmetic (the first pass adds zeros to a spare
+      // row); with 6 points per lane (three CTAs per SM) it runs in place.
+      constexpr bool DEFER = (P == 8);
+      double pa_[4] = {0.0, 0.0, 0.0, 0.0}, pb_[4] = {0.0, 0.0, 0.0, 0.0};
+      double* app = acc_w + (size_t)(NS - 2) * 16 + (b0 ? 16 : 0) + grp * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);   // spare rows
+      for (int s = 0; s < n2; s += 2) {
+        gpa += 2 * gstride;
+        gpb += 2 * gstride;
+        const double ha0 = __ldg(gpa), hb0 = __ldg(gpb);                 // rows up to LMAX + 3 exist
+        const double ha1 = __ldg(gpa + gstride), hb1 = __ldg(gpb + gstride);
+        double va[4], vb[4];
+        if (DEFER) {
+          const double r1a = __shfl_xor_sync(0xffffffffu, pa_[2], 4), r2a = __shfl_xor_sync(0xffffffffu, pa_[3], 4);
+          const double r1b = __shfl_xor_sync(0xffffffffu, pb_[2], 4), r2b = __shfl_xor_sync(0xffffffffu, pb_[3], 4);
+          step(ga0, gb0, va);
+          const double k1a = pa_[0] + r1a, k2a = pa_[1] + r2a, k1b = pb_[0] + r1b, k2b = pb_[1] + r2b;
+          const double r3a = __shfl_xor_sync(0xffffffffu, k2a, 2), r3b = __shfl_xor_sync(0xffffffffu, k2b, 2);
+          step(ga1, gb1, vb);
+          const double ma_ = k1a + r3a, mb_ = k1b + r3b;
+          const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
+          *app += k1;
+          app = ap;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            pa_[i] = va[i];
+            pb_[i] = vb[i];
+          }
+        } else {
+          step(ga0, gb0, va);
+          step(ga1, gb1, vb);
+          if (q.dbg & 4) {
+            *ap += (va[0] + va[1]) + (va[2] + va[3]) + (vb[0] + vb[1]) + (vb[2] + vb[3]);
+          } else {
+            const double k1a = va[0] + __shfl_xor_sync(0xffffffffu, va[2], 4);
+            const double k2a = va[1] + __shfl_xor_sync(0xffffffffu, va[3], 4);
+            const double k1b = vb[0] + __shfl_xor_sync(0xffffffffu, vb[2], 4);
+            const double k2b = vb[1] + __shfl_xor_sync(0xffffffffu, vb[3], 4);
+            const double ma_ = k1a + __shfl_xor_sync(0xffffffffu, k2a, 2);
+            const double mb_ = k1b + __shfl_xor_sync(0xffffffffu, k2b, 2);
+            const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
+            *ap += k1;
+          }
+        }
+        ga0 = ha0; gb0 = hb0; ga1 = ha1; gb1 = hb1;
+        ap += 32;
+      }
+      if (DEFER) {
+        const double k1a = pa_[0] + __shfl_xor_sync(0xffffffffu, pa_[2], 4);
+        const double k2a = pa_[1] + __shfl_xor_sync(0xffffffffu, pa_[3], 4);
+        const double k1b = pb_[0] + __shfl_xor_sync(0xffffffffu, pb_[2], 4);
+        const double k2b = pb_[1] + __shfl_xor_sync(0xffffffffu, pb_[3], 4);
+        const double ma_ = k1a + __shfl_xor_sync(0xffffffffu, k2a, 2);
+        const double mb_ = k1b + __shfl_xor_sync(0xffffffffu, k2b, 2);
+        const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
+        *app += k1;
+      }
+    };
+    walk(mqa, warp, nA2, 0);
+    walk(mqb, 7 - warp, nB2, nA2);
+  }
+  __syncwarp();
+  // this CTA's partial sums: the (l >= m) entries of the two walks
+  double* slot = q.slots + ((size_t)blockIdx.x * q.nbatch + t) * 2 * (L + 1) * (q.mmax + 1);
+  const size_t plane = (size_t)(L + 1) * (q.mmax + 1);
+  for (int wk = 0; wk < 2; ++wk) {
+    const int mq = wk ? mqb : mqa, n = wk ? nB : nA, row0 = wk ? nA2 : 0;
+    for (int i = lane; i < n * 16; i += 32) {
+      const int s = i >> 4, e = i & 15;
+      const int l = mq + s, m = mq + (e >> 1);
+      if (m <= q.mmax && l >= m)
+        slot[(size_t)(e & 1) * plane + (size_t)l * (q.mmax + 1) + m] = acc_w[(size_t)(row0 + s) * 16 + e];
+    }
+  }
+}
+
 // grid (lmax+1, nbatch), 1024 threads: out = dfactor[l] * sum over CTA partials.  Sixteen interleaved
 // partial sums per (l, m) keep independent loads in flight; they are combined in a fixed order.
 constexpr int PR_GROUPS = 16;
@@ -582,7 +961,11 @@ __global__ void __launch_bounds__(64 * PR_GROUPS) points_reduce_kernel(const Poi
         for (int j = 0; j < PR_GROUPS; j += 2 * w) v[j] += v[j + w];
       }
       const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
-      const double r = (m <= l) ? v[0] * df : 0.0;
+      double r = 0.0;
+      if (m <= l) {
+        r = v[0] * df;
+        if (q.scale != nullptr) r *= __ldg(q.scale + (size_t)l * q.Mpad + m);
+      }
       if (grp == 0) q.clm[o] = r; else q.slm[o] = r;
     }
     __syncthreads();
@@ -597,7 +980,7 @@ namespace {
 
 struct PointLayout {
   long long npad;
-  int Mpad, ncta_p, batches_per_cta, n_mtiles;
+  int Mpad, ncta_p, ncta_max, batches_per_cta, n_mtiles;
   size_t off_W, off_x, off_u, off_E, off_df, off_slots, total;
 };
 
@@ -611,6 +994,10 @@ PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num
   y.ncta_p = (int)std::min<long long>(nbatches, std::max<long long>(want, 1));
   y.batches_per_cta = (int)((nbatches + y.ncta_p - 1) / y.ncta_p);
   y.ncta_p = (int)((nbatches + y.batches_per_cta - 1) / y.batches_per_cta);
+  // the fused kernel runs up to three CTAs per SM on tiles of at least 48 points
+  y.ncta_max = (int)std::max<long long>(
+      y.ncta_p, std::min<long long>((npts + 47) / 48,
+                                    std::max<long long>(1, 3LL * num_sms / (y.n_mtiles * (long long)nbatch))));
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 31) / 32 * 32; return r; };
   y.off_W = take((size_t)nbatch * (lmax + 1) * y.npad);
@@ -618,7 +1005,7 @@ PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num
   y.off_u = take((size_t)y.npad);
   y.off_E = take(2 * (size_t)(mmax + 1) * y.npad);
   y.off_df = take((size_t)lmax + 1);
-  y.off_slots = take((size_t)y.ncta_p * nbatch * 2 * (lmax + 1) * (mmax + 1));
+  y.off_slots = take((size_t)y.ncta_max * nbatch * 2 * (lmax + 1) * (mmax + 1));
   y.total = o * sizeof(double);
   return y;
 }
@@ -644,8 +1031,10 @@ int point_tables(int device, int lmax, int mmax, int Mpad, const double** out) {
     return MHB200_OK;
   }
   const size_t nf = (size_t)(lmax + 1) * Mpad;
-  std::vector<double> tab(2 * nf + (size_t)Mpad + 2 * (size_t)(lmax + 1), 0.0);
+  const size_t ng = (size_t)(lmax + 4) * Mpad;          // the fused kernel reads up to three zero rows past LMAX
+  std::vector<double> tab(3 * nf + ng + (size_t)Mpad + 2 * (size_t)(lmax + 1), 0.0);
   double *f1 = tab.data(), *f2 = f1 + nf, *pmm = f2 + nf, *dc1 = pmm + Mpad, *dc2 = dc1 + (lmax + 1);
+  double *gl = dc2 + (lmax + 1), *sc = gl + ng;
   for (int l = 2; l <= lmax; ++l) {
     const double dl = (double)l;
     f1[(size_t)l * Mpad] = sqrt(2.0 * dl - 1.0) * sqrt(2.0 * dl + 1.0) / dl;
@@ -677,6 +1066,35 @@ int point_tables(int device, int lmax, int mmax, int Mpad, const double** out) {
     const double dl = (double)l;
     dc1[l] = (2.0 * dl + 1.0) / (dl + 1.0);
     dc2[l] = dl / (dl + 1.0);
+  }
+  // one-multiplier form of the same recursion (points_fused_kernel): q_l = Plm / (u^m c_lm) with
+  // c_mm = Pmm / u^m, c_(m+1)m = sqrt(2m+3) c_mm, c_lm = f2_lm c_(l-2)m, so that
+  // q_m = 1, q_(m+1) = x, q_l = (x g_lm) q_(l-1) - q_(l-2), g_lm = f1_lm c_(l-1)m / c_lm.
+  // Formed in extended precision and rounded once.
+  {
+    long double cmm = 1.0L;
+    for (int m = 0; m <= mmax; ++m) {
+      if (m == 1) cmm = sqrtl(3.0L);
+      if (m > 1) cmm = cmm * sqrtl(2.0L * m + 1.0L) / sqrtl(2.0L * m);
+      long double c2 = cmm, c1 = 0.0L;
+      sc[(size_t)m * Mpad + m] = (double)cmm;
+      if (m + 1 <= lmax) {
+        c1 = cmm * sqrtl(2.0L * m + 3.0L);
+        sc[(size_t)(m + 1) * Mpad + m] = (double)c1;
+        gl[(size_t)(m + 1) * Mpad + m] = 1.0;
+      }
+      for (int l = m + 2; l <= lmax; ++l) {
+        const long double dl = l, dm = m;
+        const long double a = sqrtl((2.0L * dl + 1.0L) * (2.0L * dl - 1.0L) / ((dl + dm) * (dl - dm)));
+        const long double b = sqrtl((2.0L * dl + 1.0L) * (dl - dm - 1.0L) * (dl + dm - 1.0L) /
+                                    ((2.0L * dl - 3.0L) * (dl + dm) * (dl - dm)));
+        const long double c = b * c2;
+        gl[(size_t)l * Mpad + m] = (double)(a * c1 / c);
+        sc[(size_t)l * Mpad + m] = (double)c;
+        c2 = c1;
+        c1 = c;
+      }
+    }
   }
   double* dev = nullptr;
   MHB_CUDA(cudaMalloc((void**)&dev, tab.size() * sizeof(double)));
@@ -776,6 +1194,60 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
   q.ncta_p = y.ncta_p;
   q.clm = clm_out;
   q.slm = slm_out;
+  q.gl = q.dc2 + (lmax + 1);
+  q.scale = nullptr;
+  q.tiles_per_cta = 0;
+  q.tiles_rem = 0;
+  q.fused_steps = 0;
+  q.dbg = 0;
+  if (const char* e = getenv("MHB200_POINTS_DBG")) q.dbg = atoi(e);
+
+  // fused kernel (one launch from the point arrays to the partial sums) wherever two of its CTAs fit on an SM
+  {
+    int steps = 0;
+    for (int j = 0; j < y.n_mtiles; ++j)
+      for (int w = 0; w < 4; ++w)
+        steps = std::max(steps, fused_walk_steps(lmax, mmax, j * PF_ORD, w) +
+                                    fused_walk_steps(lmax, mmax, j * PF_ORD, 7 - w));
+    steps += 2;                                                // two spare accumulator rows
+    const char* env = getenv("MHB200_POINTS_FUSED");
+    const bool want = !(env && env[0] == '0');
+    const int P = (env && env[0] == '6') ? 6 : 8;             // points per lane (A/B switch; default 8)
+    const int TILE = 8 * P;
+    const size_t smem_fused = ((size_t)4 * steps * 16 + 2 * ((lmax + 2) & ~1) +
+                               (size_t)(lmax + 2 + PF_AUX) * TILE) * sizeof(double);
+    const size_t smem_cap = (P == 8) ? (size_t)(228 * 1024) / 2 - 1024 : (size_t)(228 * 1024) / 3 - 1024;
+    if (want && smem_fused <= smem_cap) {
+      const long long ntiles = (npts + TILE - 1) / TILE;
+      const long long slots_cta = (P == 8) ? 2 : 3;
+      const long long cap = std::max<long long>(1, slots_cta * sms / (y.n_mtiles * (long long)nbatch));
+      const long long ctas = std::max<long long>(1, std::min<long long>(ntiles, std::min<long long>(cap, y.ncta_max)));
+      q.tiles_per_cta = (int)(ntiles / ctas);
+      q.tiles_rem = (int)(ntiles % ctas);
+      q.ncta_p = (int)ctas;
+      q.fused_steps = steps;
+      q.scale = q.gl + (size_t)(lmax + 4) * Mpad;
+      dim3 grid(q.ncta_p, y.n_mtiles, nbatch);
+      profile_begin(st);
+      if (P == 8) {
+        MHB_CUDA(cudaFuncSetAttribute(points_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_fused));
+        points_fused_kernel<8><<<grid, PF_NT, smem_fused, st>>>(q);
+      } else {
+        MHB_CUDA(cudaFuncSetAttribute(points_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_fused));
+        points_fused_kernel<6><<<grid, PF_NT, smem_fused, st>>>(q);
+      }
+      profile_end(st);
+      g_launches.fetch_add(1);
+      MHB_CUDA(cudaGetLastError());
+      dim3 rgrid(lmax + 1, nbatch);
+      points_reduce_kernel<<<rgrid, 64 * PR_GROUPS, 0, st>>>(q, dfs);
+      g_launches.fetch_add(1);
+      MHB_CUDA(cudaGetLastError());
+      return MHB200_OK;
+    }
+  }
 
   {
     const int nmg = (mmax + PT_MGROUP) / PT_MGROUP;
