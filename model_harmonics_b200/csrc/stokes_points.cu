@@ -29,6 +29,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -66,8 +67,8 @@ struct PointParams {
   const double* gl;             // [(lmax+1)][Mpad] multipliers of the one-multiplier recursion (points_fused_kernel)
   const double* scale;          // [(lmax+1)][Mpad] its normalisation c_lm, applied by the reduce kernel (or null)
   int tiles_per_cta, tiles_rem, fused_steps;   // CTA b takes tiles_per_cta (+1 if b < tiles_rem) consecutive tiles
-  int dbg;                      // timing experiments only (MHB200_POINTS_DBG): 1 skip the tile preparation after the
-                                // first tile, 2 skip the trig factors after the first tile, 4 skip the reduction
+  unsigned long long* flag;     // set to `gen` by the fast kernel when an angle is outside its short sincos
+  unsigned long long gen;       // (a fresh value per call: the word never has to be cleared)
 };
 
 constexpr int DF_MAX = 448;      // degree factors travel as kernel parameters up to this many
@@ -575,25 +576,32 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_staged(const PointPa
 //    divergence), and warps only meet at the tile boundaries.
 //  * The 8 lanes of a duo are combined every two steps by a transposed reduction (7 exchanges for 8 sums);
 //    each lane then owns one accumulator in shared memory.
-//  * Tile boundary: 64 threads walk the disc-weight recursion of one point each, in the reference's exact
-//    operation order (as points_prepare_kernel), straight into the shared-memory tile, with cos(theta), u
-//    and phi as three more rows.
+//  * The next tile is prepared WHILE this one is contracted (two tile buffers) by four PRODUCER warps of the
+//    same CTA: warps 4-5 walk the disc-weight recursion of one point per thread -- the reference's exact
+//    operation order, as points_prepare_kernel -- and warps 6-7 write the per-point rows (cos theta, u, phi,
+//    e^{i phi}, u^(8k)); both are latency-bound and short, and then sleep at the tile's single barrier.  The
+//    register file is split to match (setmaxnreg): 216 registers per contraction thread, 40 per producer.
+//  * e^{i m phi} of the ROUNDED product m phi (what the reference's exp(1j m phi) sees) costs one short
+//    sincos per (point, duo) -- Cody-Waite + Taylor, coefficients in the constant bank -- and one rotation by
+//    e^{i phi} for the duo's second order, with the rounding difference of the two products applied exactly.
 // ---------------------------------------------------------------------------------------
-constexpr int PF_NT = 128;       // 4 warps
+constexpr int PF_NT = 256;       // 4 contraction warps + 4 producer warps
+constexpr int PF_REGS_MAIN = 216, PF_REGS_PROD = 40;   // 128 x (216 + 40) = 256 x 128 registers per CTA
+constexpr int PF_P = 8;          // points per lane
+constexpr int PF_TILE = 64;      // points per tile: 8 lanes x 8 points
 constexpr int PF_ORD = 64;       // orders per CTA (4 warps x 2 walks x 8 orders)
 constexpr int PF_AUX = 13;       // per-point rows next to the weights: x, phi, cos phi, sin phi, u, u^(m0 + 8k) k = 0..7
 
-// rows of one warp's accumulators / multipliers: both walks, each rounded up to an even number of steps
+// rows of one warp's accumulators: both walks, each rounded up to an even number of steps
 __host__ __device__ inline int fused_walk_steps(int lmax, int mmax, int m0, int quad) {
   const int mq = m0 + 8 * quad;
   const int n = (mq <= mmax) ? (lmax + 1 - mq) : 0;
   return (n + 1) & ~1;
 }
 
-template <int P>
-__device__ __forceinline__ void pf_load(const double* row, double (&v)[P]) {
+__device__ __forceinline__ void pf_load(const double* row, double (&v)[PF_P]) {
 #pragma unroll
-  for (int k = 0; k < P / 2; ++k) {
+  for (int k = 0; k < PF_P / 2; ++k) {
     const double2 a = *reinterpret_cast<const double2*>(row + 16 * k);
     v[2 * k] = a.x;
     v[2 * k + 1] = a.y;
@@ -612,6 +620,7 @@ __constant__ double PF_SC[20] = {
     // cos: -1/2!, 1/4!, ... 1/16!  (of 1 + z (c0 + z (c1 + ...)))
     -0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0};
 __constant__ double PF_C16 = 1.0 / 20922789888000.0;
+constexpr double PF_TRIG_MAX = 500000.0;      // beyond this the general-purpose functions take over
 
 __device__ __forceinline__ void pf_sincos(const double a, double& sn, double& cs) {
   const double t = fma(a, PF_SC[0], PF_SC[1]);
@@ -635,10 +644,85 @@ __device__ __forceinline__ void pf_sincos(const double a, double& sn, double& cs
   cs = ((n + 1) & 2) ? -cv : cv;
 }
 
-template <int P>
-__global__ void __launch_bounds__(PF_NT, (P == 8) ? 2 : 3) points_fused_kernel(const PointParams q) {
-  constexpr int TILE = 8 * P;                        // points per tile: 8 lanes x P points
-  extern __shared__ __align__(16) double acc_s[];   // acc [4][NS][16] | dc [2][L+1] | tile [L+2+AUX][TILE]
+// state of one point's disc-weight recursion (gen_point_pressure.py:126-147), advanced one degree at a time
+struct DiscChain {
+  double alpha, PG, r, Pm1, Pl, pw;
+  bool live;
+};
+
+__device__ __forceinline__ void chain_start(DiscChain& c, const PointParams& q, const int t, const long long p) {
+  c.live = (p < q.npts);
+  c.alpha = c.PG = c.r = 0.0;
+  if (c.live) {
+    c.alpha = __dsub_rn(1.0, __ddiv_rn(q.area[p], q.area_denom));
+    c.PG = __ddiv_rn(q.P[(size_t)t * q.npts + p], q.G[p * q.Gs]);
+    c.r = __ddiv_rn(q.R[p * q.Rs], q.rad_e);
+  }
+  c.Pm1 = 1.0;
+  c.Pl = 1.0;
+  c.pw = __dmul_rn(c.r, c.r);
+}
+
+// W_l of the chain's point (the reference's operation order, no FMA contraction); dc = ((2l+1)/(l+1), l/(l+1))
+__device__ __forceinline__ double chain_step(DiscChain& c, const double2 dc) {
+  const double Pp1 = __dsub_rn(__dmul_rn(__dmul_rn(dc.x, c.alpha), c.Pl), __dmul_rn(dc.y, c.Pm1));
+  const double Pdisc = __dmul_rn(__dsub_rn(c.Pm1, Pp1), 0.5);
+  const double w = __dmul_rn(__dmul_rn(Pdisc, c.PG), c.pw);
+  c.pw = __dmul_rn(c.pw, c.r);
+  c.Pm1 = c.Pl;
+  c.Pl = Pp1;
+  return c.live ? w : 0.0;
+}
+
+// per-point rows of one tile column: x, phi, cos phi, sin phi, u, u^(m0 + 8k)
+template <bool SAFE>
+__device__ __forceinline__ void aux_column(double* col, const PointParams& q, const long long p, const int m0) {
+  double x = 0.0, u = 1.0, ph = 0.0, cp = 1.0, sp = 0.0;
+  if (p < q.npts) {
+    const double th = q.theta[p];
+    ph = q.phi[p];
+    if (SAFE) {
+      x = cos(th);
+      sincos(ph, &sp, &cp);
+    } else {
+      // an angle (or its largest multiple in this CTA) outside the short sincos: the safe kernel redoes the call
+      if (!(fabs(th) < PF_TRIG_MAX) || !(fabs(ph) * (double)(m0 + PF_ORD) < PF_TRIG_MAX)) *q.flag = q.gen;
+      double sth;
+      pf_sincos(th, sth, x);
+      pf_sincos(ph, sp, cp);
+    }
+    u = sqrt(1.0 - x * x);
+    if (u == 0.0) u = 2.220446049250313e-16;
+  }
+  col[0 * PF_TILE] = x;
+  col[1 * PF_TILE] = ph;
+  col[2 * PF_TILE] = cp;
+  col[3 * PF_TILE] = sp;
+  col[4 * PF_TILE] = u;
+  double pw = 1.0, bb = u;
+  for (int k = m0; k; k >>= 1) {
+    if (k & 1) pw *= bb;
+    bb *= bb;
+  }
+  const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    col[(5 + k) * PF_TILE] = pw;
+    pw *= u8;
+  }
+}
+
+// SAFE = false: the kernel as described.  SAFE = true: the same walk with the general-purpose cos / sincos for
+// every angle, one CTA per SM and no register hand-over (ptxas 12.9 does not survive a device-function call
+// under setmaxnreg); it is launched after the fast kernel on every call and returns at once unless that one met
+// an angle beyond PF_TRIG_MAX (no real longitude does), in which case it overwrites all the partial sums.
+template <bool SAFE>
+__global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const PointParams q) {
+  constexpr int P = PF_P, TILE = PF_TILE;
+  if (SAFE) {
+    if (*q.flag != q.gen) return;
+  }
+  extern __shared__ __align__(16) double acc_s[];   // acc [4][NS][16] | dc [L+1][2] | 2 x tile [L+3+AUX][TILE]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = lane >> 3, j = lane & 7;
   const int t = blockIdx.z;
@@ -647,174 +731,151 @@ __global__ void __launch_bounds__(PF_NT, (P == 8) ? 2 : 3) points_fused_kernel(c
   const int NS = q.fused_steps;
   double* acc_w = acc_s + (size_t)warp * NS * 16;
   double* dc_s = acc_s + (size_t)4 * NS * 16;
-  double* tile = dc_s + 2 * ((L + 2) & ~1);
-  double* aux = tile + (size_t)(L + 2) * TILE;       // rows 0 .. L: weights, row L + 1: zeros
-  const int mqa = m0 + 8 * warp, mqb = m0 + 8 * (7 - warp);
-  const int nA = (mqa <= q.mmax) ? (L + 1 - mqa) : 0, nB = (mqb <= q.mmax) ? (L + 1 - mqb) : 0;
-  const int nA2 = (nA + 1) & ~1, nB2 = (nB + 1) & ~1;
-
-  for (int i = lane; i < NS * 16; i += 32) acc_w[i] = 0.0;
-  for (int i = tid; i <= L; i += PF_NT) {
-    dc_s[2 * i] = __ldg(q.dc1 + i);
-    dc_s[2 * i + 1] = __ldg(q.dc2 + i);
-  }
-  for (int i = tid; i < TILE; i += PF_NT) tile[(size_t)(L + 1) * TILE + i] = 0.0;   // the step past LMAX of an odd walk
+  double* tiles = dc_s + 2 * ((L + 2) & ~1);
+  // rows 0 .. L: weights, L + 1: zeros, L + 2: scratch, then the per-point rows
+  const size_t tile_doubles = (size_t)(L + 3 + PF_AUX) * TILE;
+  const size_t aux_off = (size_t)(L + 3) * TILE;
+  const int mq2[2] = {m0 + 8 * warp, m0 + 8 * (7 - warp)};
+  const int n2_[2] = {fused_walk_steps(L, q.mmax, m0, warp), fused_walk_steps(L, q.mmax, m0, 7 - warp)};
 
   const long long tile0 = (long long)blockIdx.x * q.tiles_per_cta + min((int)blockIdx.x, q.tiles_rem);
   const long long tile1 = tile0 + q.tiles_per_cta + (((int)blockIdx.x < q.tiles_rem) ? 1 : 0);
+
+  if (warp >= 4) {
+    // ---- producers: tile tb + 1 into the other buffer while the contraction warps work on tile tb ----
+    if (!SAFE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PF_REGS_PROD));
+    const int pt = tid - 128;
+    const int pcol = pt & 63;
+    for (int i = pt; i <= L; i += 128) {
+      dc_s[2 * i] = __ldg(q.dc1 + i);
+      dc_s[2 * i + 1] = __ldg(q.dc2 + i);
+    }
+    for (int i = pt; i < 2 * TILE; i += 128)           // the step past LMAX of an odd walk reads zeros
+      tiles[(size_t)(i / TILE) * tile_doubles + (size_t)(L + 1) * TILE + (i % TILE)] = 0.0;
+    asm volatile("bar.sync 1, 128;" ::: "memory");     // dc_s is in place (producers only)
+    for (long long tb = tile0; tb <= tile1; ++tb) {
+      // pass tb prepares tile tb (the first pass before any contraction, the last one has nothing to prepare)
+      if (tb < tile1) {
+        double* tn = tiles + (size_t)((int)(tb - tile0) & 1) * tile_doubles;
+        const long long p = tb * TILE + pcol;
+        if (pt < 64) {
+          DiscChain ch;
+          chain_start(ch, q, t, p);
+          // blocks of four degrees: the loop-carried part (two dependent operations per degree) first, then
+          // the four independent tails, so that their latencies overlap
+          for (int l0 = 0; l0 <= L; l0 += 4) {
+            double w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              w[k] = chain_step(ch, *reinterpret_cast<const double2*>(dc_s + 2 * min(l0 + k, L)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (l0 + k <= L) tn[(size_t)(l0 + k) * TILE + pcol] = w[k];
+          }
+        } else {
+          aux_column<SAFE>(tn + aux_off + pcol, q, p, m0);
+        }
+        // the inputs of the tile after towards L2
+        const long long pn = p + TILE;
+        if (tb + 1 < tile1 && pn < q.npts) {
+          if (pt < 64) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q.area + pn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q.P + (size_t)t * q.npts + pn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q.G + pn * q.Gs));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q.R + pn * q.Rs));
+          } else {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q.theta + pn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q.phi + pn));
+          }
+        }
+      }
+      __syncthreads();     // tile tb is complete / the contraction warps are done with tile tb - 1
+    }
+    return;
+  }
+
+  // ---- contraction warps ----
+  if (!SAFE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PF_REGS_MAIN));
+  for (int i = lane; i < NS * 16; i += 32) acc_w[i] = 0.0;
   // Roles inside a duo's 8 lanes (bits of j): b2 picks which of the two orders is the lane's slot A (the other is
   // slot B), b1 which of cos / sin is the "first" component.  The lanes combine their sums by a transposed
   // reduction in which every lane KEEPS its slot-A / first sums and SENDS its slot-B / second sums: the partner
   // across b2 (b1) has the roles swapped, so no value has to be selected.  Only the last exchange (b0: which of
   // the two steps) selects.  The lane ends up with: order ma + b2, component b1, step s + b0.
   const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
-  double* acc_mine = acc_w + (b0 ? 16 : 0) + grp * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);
-  const int pcol = (tid & 63);                       // the point of the tile this thread prepares
+  const int acc_lane = (b0 ? 16 : 0) + grp * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);
 
   for (long long tb = tile0; tb < tile1; ++tb) {
-    __syncthreads();       // every warp is done with the previous tile (first pass: tables are in place)
-    if (!((q.dbg & 1) && tb != tile0)) {
-      const long long p = tb * TILE + pcol;
-      const bool live = (pcol < TILE) && (p < q.npts);
-      if (tb + 1 < tile1 && pcol < TILE && p + TILE < q.npts) {
-        // the next tile's inputs towards L2 / L1 while this one is contracted
-        const long long pn = p + TILE;
-        if (tid < 64) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.area + pn));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.P + (size_t)t * q.npts + pn));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.G + pn * q.Gs));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.R + pn * q.Rs));
-        } else {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.theta + pn));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q.phi + pn));
-        }
-      }
-      if (tid < 64) {
-        // warps 0, 1: the disc weights, gen_point_pressure.py:126-147 in the reference's operation order
-        // (see points_prepare_kernel)
-        if (pcol < TILE) {
-          double* col = tile + pcol;
-          if (live) {
-            const double alpha = __dsub_rn(1.0, __ddiv_rn(q.area[p], q.area_denom));
-            const double PG = __ddiv_rn(q.P[(size_t)t * q.npts + p], q.G[p * q.Gs]);
-            const double r = __ddiv_rn(q.R[p * q.Rs], q.rad_e);
-            double Pm1 = 1.0, Pl = 1.0;
-            double pw = __dmul_rn(r, r);
-            // blocks of four degrees: the loop-carried part (two dependent operations per degree) first, then the
-            // four independent tails, so that their latencies overlap
-            for (int l0 = 0; l0 <= L; l0 += 4) {
-              double pm[4], pp[4], pk[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const double2 c = *reinterpret_cast<const double2*>(dc_s + 2 * min(l0 + k, L));
-                const double Pp1 = __dsub_rn(__dmul_rn(__dmul_rn(c.x, alpha), Pl), __dmul_rn(c.y, Pm1));
-                pm[k] = Pm1;
-                pp[k] = Pp1;
-                pk[k] = pw;
-                pw = __dmul_rn(pw, r);
-                Pm1 = Pl;
-                Pl = Pp1;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const double Pdisc = __dmul_rn(__dsub_rn(pm[k], pp[k]), 0.5);
-                if (l0 + k <= L) col[(size_t)(l0 + k) * TILE] = __dmul_rn(__dmul_rn(Pdisc, PG), pk[k]);
-              }
-            }
-          } else {
-            for (int l = 0; l <= L; ++l) col[(size_t)l * TILE] = 0.0;
-          }
-        }
-      } else if (pcol < TILE) {
-        // warps 2, 3: the per-point rows
-        double* col = aux + pcol;
-        double x = 0.0, u = 1.0, ph = 0.0, cp = 1.0, sp = 0.0;
-        if (live) {
-          x = cos(q.theta[p]);
-          u = sqrt(1.0 - x * x);
-          if (u == 0.0) u = 2.220446049250313e-16;
-          ph = q.phi[p];
-          sincos(ph, &sp, &cp);
-        }
-        col[0 * TILE] = x;
-        col[1 * TILE] = ph;
-        col[2 * TILE] = cp;
-        col[3 * TILE] = sp;
-        col[4 * TILE] = u;
-        // u^(m0 + 8k), k = 0 .. 7
-        double pw = 1.0, bb = u;
-        for (int k = m0; k; k >>= 1) {
-          if (k & 1) pw *= bb;
-          bb *= bb;
-        }
-        const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          col[(5 + k) * TILE] = pw;
-          pw *= u8;
-        }
-      }
-    }
-    __syncthreads();
+    __syncthreads();       // this tile's buffer is complete, and every warp is done with the other one
+    const int cur = (int)(tb - tile0) & 1;
+    const double* tile = tiles + (size_t)cur * tile_doubles;
+    const double* aux = tile + aux_off;
 
     double x[P];
-    pf_load<P>(aux + 2 * j, x);
+    pf_load(aux + 2 * j, x);
 
-    // one walk of this warp: orders [mq, mq + 8), degrees mq .. mq + n2 - 1, accumulator / multiplier rows from row0
-    auto walk = [&](const int mq, const int quad, const int n2, const int row0) {
-      if (n2 == 0) return;
+    // the two walks of this warp: orders [mq, mq + 8), degrees mq .. mq + n2 - 1
+    int row0 = 0;
+#pragma unroll 1
+    for (int wk = 0; wk < 2; ++wk) {
+      const int mq = mq2[wk], n2 = n2_[wk];
+      if (n2 == 0) continue;
+      const int quad = wk ? 7 - warp : warp;
       const int ma = mq + 2 * grp;               // this lane's orders: ma, ma + 1
       // slot A / B: first and second trig factor, recursion state
       double fa[P], ga[P], fb[P], gb[P], pa1[P], pa2[P], pb1[P], pb2[P];
-      if ((q.dbg & 2) && tb != tile0) {
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-          fa[i] = ga[i] = fb[i] = gb[i] = 0.5;
-          pa1[i] = pb2[i] = 0.0;
-          pa2[i] = pb1[i] = 1.0;
-        }
-      } else {
-        double ph[P], cp[P], sp[P], u[P], um[P];
-        pf_load<P>(aux + 1 * TILE + 2 * j, ph);
-        pf_load<P>(aux + 2 * TILE + 2 * j, cp);
-        pf_load<P>(aux + 3 * TILE + 2 * j, sp);
-        pf_load<P>(aux + 4 * TILE + 2 * j, u);
-        pf_load<P>(aux + (size_t)(5 + quad) * TILE + 2 * j, um);
+      {
         const bool live_a = (ma <= q.mmax), live_b = (ma + 1 <= q.mmax);
         // seeds: an order that starts d steps into the walk (d = 2 grp for ma, 2 grp + 1 for ma + 1) arrives at
         // (q_(m-1), q_m) = (0, 1) on time
         const double sgn = (grp & 1) ? 1.0 : -1.0;
         const double dma = (double)ma, dmb = (double)(ma + 1);
+        const double* ax = aux + 2 * j;
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-          // u^ma = u^mq u^(2 grp)
-          const double u2 = u[i] * u[i];
-          const double f = ((grp & 1) ? u2 : 1.0) * ((grp & 2) ? u2 * u2 : 1.0);
-          const double pwa = live_a ? um[i] * f : 0.0;
-          const double pwb = live_b ? pwa * u[i] : 0.0;
-          // gen_point_pressure.py:186-188: exp(1j * (m * phi)) of the ROUNDED product, for both orders.
-          // Order ma directly; order ma + 1 by one rotation: fl((ma+1) phi) = fl(ma phi) + phi + d with d formed
-          // exactly (both differences are exact), cos(a + phi + d) = cos(a + phi) - d sin(a + phi).
-          const double a = dma * ph[i], a2 = dmb * ph[i];
-          double sv, cv;
-          if (fabs(a2) < 500000.0) {
-            pf_sincos(a, sv, cv);
-          } else {
-            sincos(a, &sv, &cv);
+        for (int k = 0; k < P / 2; ++k) {
+          const double2 ph2 = *reinterpret_cast<const double2*>(ax + 1 * TILE + 16 * k);
+          const double2 cp2 = *reinterpret_cast<const double2*>(ax + 2 * TILE + 16 * k);
+          const double2 sp2 = *reinterpret_cast<const double2*>(ax + 3 * TILE + 16 * k);
+          const double2 u2_ = *reinterpret_cast<const double2*>(ax + 4 * TILE + 16 * k);
+          const double2 um2 = *reinterpret_cast<const double2*>(ax + (size_t)(5 + quad) * TILE + 16 * k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = 2 * k + h;
+            const double ph = h ? ph2.y : ph2.x, cp = h ? cp2.y : cp2.x, sp = h ? sp2.y : sp2.x;
+            const double u = h ? u2_.y : u2_.x, um = h ? um2.y : um2.x;
+            // u^ma = u^mq u^(2 grp)
+            const double uu = u * u;
+            const double f = ((grp & 1) ? uu : 1.0) * ((grp & 2) ? uu * uu : 1.0);
+            const double pwa = live_a ? um * f : 0.0;
+            const double pwb = live_b ? pwa * u : 0.0;
+            // gen_point_pressure.py:186-188: exp(1j * (m * phi)) of the ROUNDED product, for both orders.
+            // Order ma directly; order ma + 1 by one rotation: fl((ma+1) phi) = fl(ma phi) + phi + d with d
+            // formed exactly (both differences are exact), cos(a + phi + d) = cos(a + phi) - d sin(a + phi).
+            const double a = dma * ph, a2 = dmb * ph;
+            double sv, cv, c1v, s1v;
+            if (SAFE) {
+              sincos(a, &sv, &cv);
+              sincos(a2, &s1v, &c1v);
+              c1v *= pwb;
+              s1v *= pwb;
+            } else {
+              pf_sincos(a, sv, cv);
+              const double d = (a2 - a) - ph;
+              const double c2 = fma(cv, cp, -(sv * sp)), s2 = fma(sv, cp, cv * sp);
+              c1v = pwb * fma(-d, s2, c2);                                         // order ma + 1
+              s1v = pwb * fma(d, c2, s2);
+            }
+            const double c0v = pwa * cv, s0v = pwa * sv;                           // order ma
+            const double cA = b2 ? c1v : c0v, sA = b2 ? s1v : s0v, cB = b2 ? c0v : c1v, sB = b2 ? s0v : s1v;
+            fa[i] = b1 ? sA : cA;
+            ga[i] = b1 ? cA : sA;
+            fb[i] = b1 ? sB : cB;
+            gb[i] = b1 ? cB : sB;
+            pa1[i] = b2 ? sgn : 0.0;
+            pa2[i] = b2 ? 0.0 : sgn;
+            pb1[i] = b2 ? 0.0 : sgn;
+            pb2[i] = b2 ? sgn : 0.0;
           }
-          const double d = (a2 - a) - ph[i];
-          const double c2 = fma(cv, cp[i], -(sv * sp[i])), s2 = fma(sv, cp[i], cv * sp[i]);
-          const double c0v = pwa * cv, s0v = pwa * sv;                           // order ma
-          const double c1v = pwb * fma(-d, s2, c2), s1v = pwb * fma(d, c2, s2);  // order ma + 1
-          const double cA = b2 ? c1v : c0v, sA = b2 ? s1v : s0v, cB = b2 ? c0v : c1v, sB = b2 ? s0v : s1v;
-          fa[i] = b1 ? sA : cA;
-          ga[i] = b1 ? cA : sA;
-          fb[i] = b1 ? sB : cB;
-          gb[i] = b1 ? cB : sB;
-          pa1[i] = b2 ? sgn : 0.0;
-          pa2[i] = b2 ? 0.0 : sgn;
-          pb1[i] = b2 ? 0.0 : sgn;
-          pb2[i] = b2 ? sgn : 0.0;
         }
       }
       const double* wrow = tile + (size_t)mq * TILE + 2 * j;
@@ -824,11 +885,11 @@ __global__ void __launch_bounds__(PF_NT, (P == 8) ? 2 : 3) points_fused_kernel(c
       const double* gpb = q.gl + (size_t)mq * q.Mpad + ma + (b2 ? 0 : 1);
       const size_t gstride = (size_t)q.Mpad;
       double ga0 = __ldg(gpa), gb0 = __ldg(gpb), ga1 = __ldg(gpa + gstride), gb1 = __ldg(gpb + gstride);
-      double* ap = acc_mine + (size_t)row0 * 16;
+      double* ap = acc_w + (size_t)row0 * 16 + acc_lane;
       // one degree: v = {A first, A second, B first, B second}
       auto step = [&](const double gA, const double gB, double (&v)[4]) {
         double w[P];
-        pf_load<P>(wrow, w);
+        pf_load(wrow, w);
         wrow += TILE;
         double a1 = 0.0, a2 = 0.0, b1s = 0.0, b2s = 0.0;
 #pragma unroll
@@ -848,55 +909,36 @@ __global__ void __launch_bounds__(PF_NT, (P == 8) ? 2 : 3) points_fused_kernel(c
         v[0] = a1; v[1] = a2; v[2] = b1s; v[3] = b2s;
       };
       // Transposed reduction over the duo's 8 lanes: keep slot A, receive the partner's slot B (4 exchanges), keep
-      // the first component, receive the partner's second (2), then the step (1).  With 8 points per lane there
-      // are registers to run it ONE ITERATION LATE, its exchanges placed between the two steps of the next
-      // iteration, so that the shuffle latencies overlap that arithmetic (the first pass adds zeros to a spare
-      // row); with 6 points per lane (three CTAs per SM) it runs in place.
-      constexpr bool DEFER = (P == 8);
+      // the first component, receive the partner's second (2), then the step (1).  It runs ONE ITERATION LATE,
+      // its exchanges placed between the two steps of the next iteration, so that the shuffle latencies overlap
+      // that arithmetic (the first pass adds zeros to a spare row).
       double pa_[4] = {0.0, 0.0, 0.0, 0.0}, pb_[4] = {0.0, 0.0, 0.0, 0.0};
-      double* app = acc_w + (size_t)(NS - 2) * 16 + (b0 ? 16 : 0) + grp * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);   // spare rows
+      double* app = acc_w + (size_t)(NS - 2) * 16 + acc_lane;     // spare rows
       for (int s = 0; s < n2; s += 2) {
         gpa += 2 * gstride;
         gpb += 2 * gstride;
         const double ha0 = __ldg(gpa), hb0 = __ldg(gpb);                 // rows up to LMAX + 3 exist
         const double ha1 = __ldg(gpa + gstride), hb1 = __ldg(gpb + gstride);
         double va[4], vb[4];
-        if (DEFER) {
-          const double r1a = __shfl_xor_sync(0xffffffffu, pa_[2], 4), r2a = __shfl_xor_sync(0xffffffffu, pa_[3], 4);
-          const double r1b = __shfl_xor_sync(0xffffffffu, pb_[2], 4), r2b = __shfl_xor_sync(0xffffffffu, pb_[3], 4);
-          step(ga0, gb0, va);
-          const double k1a = pa_[0] + r1a, k2a = pa_[1] + r2a, k1b = pb_[0] + r1b, k2b = pb_[1] + r2b;
-          const double r3a = __shfl_xor_sync(0xffffffffu, k2a, 2), r3b = __shfl_xor_sync(0xffffffffu, k2b, 2);
-          step(ga1, gb1, vb);
-          const double ma_ = k1a + r3a, mb_ = k1b + r3b;
-          const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
-          *app += k1;
-          app = ap;
+        const double r1a = __shfl_xor_sync(0xffffffffu, pa_[2], 4), r2a = __shfl_xor_sync(0xffffffffu, pa_[3], 4);
+        const double r1b = __shfl_xor_sync(0xffffffffu, pb_[2], 4), r2b = __shfl_xor_sync(0xffffffffu, pb_[3], 4);
+        step(ga0, gb0, va);
+        const double k1a = pa_[0] + r1a, k2a = pa_[1] + r2a, k1b = pb_[0] + r1b, k2b = pb_[1] + r2b;
+        const double r3a = __shfl_xor_sync(0xffffffffu, k2a, 2), r3b = __shfl_xor_sync(0xffffffffu, k2b, 2);
+        step(ga1, gb1, vb);
+        const double ma_ = k1a + r3a, mb_ = k1b + r3b;
+        const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
+        *app += k1;
+        app = ap;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            pa_[i] = va[i];
-            pb_[i] = vb[i];
-          }
-        } else {
-          step(ga0, gb0, va);
-          step(ga1, gb1, vb);
-          if (q.dbg & 4) {
-            *ap += (va[0] + va[1]) + (va[2] + va[3]) + (vb[0] + vb[1]) + (vb[2] + vb[3]);
-          } else {
-            const double k1a = va[0] + __shfl_xor_sync(0xffffffffu, va[2], 4);
-            const double k2a = va[1] + __shfl_xor_sync(0xffffffffu, va[3], 4);
-            const double k1b = vb[0] + __shfl_xor_sync(0xffffffffu, vb[2], 4);
-            const double k2b = vb[1] + __shfl_xor_sync(0xffffffffu, vb[3], 4);
-            const double ma_ = k1a + __shfl_xor_sync(0xffffffffu, k2a, 2);
-            const double mb_ = k1b + __shfl_xor_sync(0xffffffffu, k2b, 2);
-            const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
-            *ap += k1;
-          }
+        for (int i = 0; i < 4; ++i) {
+          pa_[i] = va[i];
+          pb_[i] = vb[i];
         }
         ga0 = ha0; gb0 = hb0; ga1 = ha1; gb1 = hb1;
         ap += 32;
       }
-      if (DEFER) {
+      {
         const double k1a = pa_[0] + __shfl_xor_sync(0xffffffffu, pa_[2], 4);
         const double k2a = pa_[1] + __shfl_xor_sync(0xffffffffu, pa_[3], 4);
         const double k1b = pb_[0] + __shfl_xor_sync(0xffffffffu, pb_[2], 4);
@@ -906,22 +948,25 @@ __global__ void __launch_bounds__(PF_NT, (P == 8) ? 2 : 3) points_fused_kernel(c
         const double k1 = (b0 ? mb_ : ma_) + __shfl_xor_sync(0xffffffffu, b0 ? ma_ : mb_, 1);
         *app += k1;
       }
-    };
-    walk(mqa, warp, nA2, 0);
-    walk(mqb, 7 - warp, nB2, nA2);
+      row0 += n2;
+    }
   }
+  __syncthreads();       // matches the producers' last pass
   __syncwarp();
   // this CTA's partial sums: the (l >= m) entries of the two walks
   double* slot = q.slots + ((size_t)blockIdx.x * q.nbatch + t) * 2 * (L + 1) * (q.mmax + 1);
   const size_t plane = (size_t)(L + 1) * (q.mmax + 1);
+  int row0 = 0;
   for (int wk = 0; wk < 2; ++wk) {
-    const int mq = wk ? mqb : mqa, n = wk ? nB : nA, row0 = wk ? nA2 : 0;
+    const int mq = mq2[wk];
+    const int n = (mq <= q.mmax) ? (L + 1 - mq) : 0;
     for (int i = lane; i < n * 16; i += 32) {
       const int s = i >> 4, e = i & 15;
       const int l = mq + s, m = mq + (e >> 1);
       if (m <= q.mmax && l >= m)
         slot[(size_t)(e & 1) * plane + (size_t)l * (q.mmax + 1) + m] = acc_w[(size_t)(row0 + s) * 16 + e];
     }
+    row0 += n2_[wk];
   }
 }
 
@@ -981,7 +1026,7 @@ namespace {
 struct PointLayout {
   long long npad;
   int Mpad, ncta_p, ncta_max, batches_per_cta, n_mtiles;
-  size_t off_W, off_x, off_u, off_E, off_df, off_slots, total;
+  size_t off_W, off_x, off_u, off_E, off_df, off_slots, off_flag, total;
 };
 
 PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num_sms) {
@@ -1006,6 +1051,7 @@ PointLayout point_layout(long long npts, int nbatch, int lmax, int mmax, int num
   y.off_E = take(2 * (size_t)(mmax + 1) * y.npad);
   y.off_df = take((size_t)lmax + 1);
   y.off_slots = take((size_t)y.ncta_max * nbatch * 2 * (lmax + 1) * (mmax + 1));
+  y.off_flag = take(4);
   y.total = o * sizeof(double);
   return y;
 }
@@ -1199,8 +1245,8 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
   q.tiles_per_cta = 0;
   q.tiles_rem = 0;
   q.fused_steps = 0;
-  q.dbg = 0;
-  if (const char* e = getenv("MHB200_POINTS_DBG")) q.dbg = atoi(e);
+  q.flag = nullptr;
+  q.gen = 0;
 
   // fused kernel (one launch from the point arrays to the partial sums) wherever two of its CTAs fit on an SM
   {
@@ -1212,15 +1258,11 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
     steps += 2;                                                // two spare accumulator rows
     const char* env = getenv("MHB200_POINTS_FUSED");
     const bool want = !(env && env[0] == '0');
-    const int P = (env && env[0] == '6') ? 6 : 8;             // points per lane (A/B switch; default 8)
-    const int TILE = 8 * P;
     const size_t smem_fused = ((size_t)4 * steps * 16 + 2 * ((lmax + 2) & ~1) +
-                               (size_t)(lmax + 2 + PF_AUX) * TILE) * sizeof(double);
-    const size_t smem_cap = (P == 8) ? (size_t)(228 * 1024) / 2 - 1024 : (size_t)(228 * 1024) / 3 - 1024;
-    if (want && smem_fused <= smem_cap) {
-      const long long ntiles = (npts + TILE - 1) / TILE;
-      const long long slots_cta = (P == 8) ? 2 : 3;
-      const long long cap = std::max<long long>(1, slots_cta * sms / (y.n_mtiles * (long long)nbatch));
+                               2 * (size_t)(lmax + 3 + PF_AUX) * PF_TILE) * sizeof(double);
+    if (want && smem_fused <= (size_t)(228 * 1024) / 2 - 1024) {
+      const long long ntiles = (npts + PF_TILE - 1) / PF_TILE;
+      const long long cap = std::max<long long>(1, 2LL * sms / (y.n_mtiles * (long long)nbatch));
       const long long ctas = std::max<long long>(1, std::min<long long>(ntiles, std::min<long long>(cap, y.ncta_max)));
       q.tiles_per_cta = (int)(ntiles / ctas);
       q.tiles_rem = (int)(ntiles % ctas);
@@ -1229,17 +1271,17 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
       q.scale = q.gl + (size_t)(lmax + 4) * Mpad;
       dim3 grid(q.ncta_p, y.n_mtiles, nbatch);
       profile_begin(st);
-      if (P == 8) {
-        MHB_CUDA(cudaFuncSetAttribute(points_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_fused));
-        points_fused_kernel<8><<<grid, PF_NT, smem_fused, st>>>(q);
-      } else {
-        MHB_CUDA(cudaFuncSetAttribute(points_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_fused));
-        points_fused_kernel<6><<<grid, PF_NT, smem_fused, st>>>(q);
-      }
+      static std::atomic<unsigned long long> generation{0x9e3779b97f4a7c15ull};
+      q.flag = reinterpret_cast<unsigned long long*>(ws + y.off_flag);
+      q.gen = generation.fetch_add(0x9e3779b97f4a7c15ull);
+      MHB_CUDA(cudaFuncSetAttribute(points_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_fused));
+      MHB_CUDA(cudaFuncSetAttribute(points_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_fused));
+      points_fused_kernel<false><<<grid, PF_NT, smem_fused, st>>>(q);
       profile_end(st);
-      g_launches.fetch_add(1);
+      points_fused_kernel<true><<<grid, PF_NT, smem_fused, st>>>(q);     // returns at once unless flagged
+      g_launches.fetch_add(2);
       MHB_CUDA(cudaGetLastError());
       dim3 rgrid(lmax + 1, nbatch);
       points_reduce_kernel<<<rgrid, 64 * PR_GROUPS, 0, st>>>(q, dfs);

@@ -76,6 +76,24 @@ def test_points_boundary_sizes(n, L, M):
     assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
 
 
+def test_points_huge_angles_take_the_safe_kernel():
+    """Longitudes / colatitudes far outside a circle (|m phi| beyond the fused kernel's short sincos) are redone by
+    the general-purpose variant of the same kernel: still the reference's exp(1j m phi) of the rounded product."""
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    P, G, R, lon, lat, AREA = syn.point_cloud(700, seed=5)
+    lon = lon + 360.0 * 2.0e5                     # phi ~ 1.3e6 rad
+    kw = dict(AREA=AREA, LMAX=40, MMAX=None, LOVE=syn.love_numbers(40))
+    A = mh.gen_point_pressure(P, G, R, lon, lat, **kw)
+    B = stokes_oracle.gen_point_pressure(P, G, R, lon, lat, **kw)
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+    # and a normal call afterwards is unaffected
+    P, G, R, lon, lat, AREA = syn.point_cloud(700, seed=6)
+    A = mh.gen_point_pressure(P, G, R, lon, lat, **kw)
+    B = stokes_oracle.gen_point_pressure(P, G, R, lon, lat, **kw)
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+
+
 @pytest.mark.parametrize('method', ['BC05', 'SW02'])
 def test_moment_path_and_direct_path_agree(monkeypatch, method):
     """The binomial-moment produce path (default at fold level 2, LMAX <= 63) against the direct powers, both
