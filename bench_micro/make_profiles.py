@@ -16,7 +16,7 @@ NAMES = {
     'c4_ka': 'pressure_moment_kernel (K_A pressure), C4 721x1440 LMAX 360',
     'c4_kb': 'legendre_moment_kernel (K_B), C4',
     'hyp': 'hypsometric_kernel<4>, 37x721x1440 float32',
-    'c2_contract': 'points_contract_staged, C2 1e5 points LMAX 60',
+    'c2_fused': 'points_fused_kernel<false>, C2 1e5 points LMAX 60',
 }
 
 

@@ -10,7 +10,7 @@ $N -k regex:legendre_moment -s 1 -c 1 -f -o gpurun_out/r2f_c3b_kb python bench_m
 $N -k regex:pressure_moment -s 1 -c 1 -f -o gpurun_out/r2f_c4_ka python bench_micro/prof_case.py c4 2 >> $LOG 2>&1
 $N -k regex:legendre_moment -s 1 -c 1 -f -o gpurun_out/r2f_c4_kb python bench_micro/prof_case.py c4 2 >> $LOG 2>&1
 $N -k regex:hypsometric -s 3 -c 1 -f -o gpurun_out/r2f_hyp python bench_micro/hyp_timing.py >> $LOG 2>&1
-$N -k regex:points_contract -s 1 -c 1 -f -o gpurun_out/r2f_c2_contract python bench_micro/prof_case.py c2 2 >> $LOG 2>&1
+$N -k regex:points_fused -s 2 -c 1 -f -o gpurun_out/r2f_c2_fused python bench_micro/prof_case.py c2 2 >> $LOG 2>&1
 for c in c3b c4 c1 c2; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r2f_launches_$c.csv python bench_micro/prof_case.py $c 2 >> $LOG 2>&1
 done

@@ -170,6 +170,9 @@ int mhb200_atmosphere_stokes_host_geoid(const mhb200_plan* plan, int dtype,
  * phi, theta, area are (npts) device arrays; P is (nbatch, npts); G and R are addressed
  * with an element stride (0 broadcasts a 1-element operand).  dfactor (host) already holds
  * 4*pi*mmwe/(1+2l).
+ * LMAX <= 61 runs one fused kernel (weights, e^{i m phi} and contraction in one launch) + the
+ * fixed-order reduce; larger LMAX a preparation kernel + contraction + reduce.  Set
+ * MHB200_POINTS_FUSED=0 to force the latter (tests compare the two).
  */
 size_t mhb200_points_workspace_bytes(int64_t npts, int nbatch, int lmax, int mmax);
 int mhb200_point_pressure_f64(int device, const double* P, const double* G, int64_t G_stride,
@@ -236,7 +239,7 @@ int mhb200_moment_layout_probe(int nf, const int* sets, int* col_grid, int* box_
 uint64_t mhb200_launch_count(void);
 
 /* measurement hook for bench.py: while enabled, every grid/point call brackets its dominant
- * kernel (stokes_ring_kernel / points_contract_kernel) with CUDA events on the launching
+ * kernel (atm_moment_kernel / stokes_ring_kernel / points_fused_kernel / ...) with CUDA events on the launching
  * stream; mhb200_profile_mean_ms() waits for them and returns the mean device time (ms) of the
  * launches recorded since enable (*n = how many), or a negative value if there were none */
 void mhb200_profile_enable(int on);

@@ -8,13 +8,18 @@
 //   C_lm + i S_lm = dfactor_l * sum_p W_l[p] * Plm(cos th_p) * e^{i m phi_p}
 //   W_l[p] = Pdisc_l(alpha_p) * (P_p/G_p) * (R_p/rad_e)^(l+2)
 //
-// Two kernels + a fixed-order reduce (the two preparation roles share one launch, points_prepare_kernel):
+// Two paths, each ending in the same fixed-order reduce (points_reduce_kernel; deterministic, no fp64 atomics):
+//
+//  A. points_fused_kernel (the default while two of its CTAs fit on an SM: LMAX <= 61): one launch from the six
+//     point arrays to the per-CTA partial sums -- see the comment above that kernel.
+//
+//  B. LMAX beyond that: points_prepare_kernel + points_contract_staged / _generic (round 1):
 //  (1) weights role: one thread per point walks the degrees.  The disc factor
 //      Pdisc_l = (P_{l-1}(alpha) - P_{l+1}(alpha))/2 is a cancellation-prone 3-term recursion
 //      (error amplified by ~1/(1-alpha) ~ npts/2), so it is evaluated in EXACTLY the
 //      reference's operation order with round-to-nearest intrinsics and no FMA contraction
 //      (the degree-only quotients (2l+1)/(l+1), l/(l+1) come from a host table: IEEE division
-//      gives the same bits on both sides).
+//      gives the same bits on both sides).  The fused kernel walks the same recursion.
 //  (2) trig role: the per (point, order) factors (u^m/1e-280) e^{i m phi}, eight orders per thread.
 //  (3) points_contract_kernel: scatter-reduce.  A lane group of 4 lanes owns one pair of
 //      orders (m, mtop-m) -- pairing gives every group the same number of degree steps -- and
@@ -23,8 +28,7 @@
 //      run ONE loop over the step index in lock step (a group changes from its first to its
 //      second order at its own step, by reloading its state), so the cross-lane sums are
 //      full-warp shuffles in uniform control flow.  Sums go to accumulators private to the lane
-//      group in shared memory; per-CTA partials go to slots that a final kernel reduces in fixed
-//      order (deterministic; no fp64 atomics).
+//      group in shared memory; per-CTA partials go to slots that the final kernel reduces.
 #include "../../include/mhb200.h"
 #include "common.cuh"
 
@@ -555,9 +559,9 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_staged(const PointPa
 }
 
 // ---------------------------------------------------------------------------------------
-// Fused variant (the default whenever two of its CTAs fit on an SM: LMAX up to ~74).  One launch reads the
-// six point arrays and writes the per-CTA partial sums; the weights W_l[p] and the factors u^m e^{i m phi}
-// never travel through HBM.
+// Fused variant (the default whenever two of its CTAs fit on an SM: LMAX <= 61, the reference's default 60
+// included).  One launch reads the six point arrays and writes the per-CTA partial sums; the weights W_l[p] and
+// the factors u^m e^{i m phi} never travel through HBM (C2: 152 MB of DRAM traffic -> 5 MB, 0.214 -> 0.143 ms).
 //
 //  * Recursion with ONE multiplier.  With q_l = Plm / (u^m c_lm), c_lm = f2_lm c_(l-2)m, the
 //    Holmes-Featherstone step p_l = x f1 p_(l-1) - f2 p_(l-2) becomes q_l = (x g_lm) q_(l-1) - q_(l-2),
@@ -574,13 +578,15 @@ __global__ void __launch_bounds__(PT_NT, 2) points_contract_staged(const PointPa
 //    [8(7-w), 8(7-w)+8) of the CTA's 64-order tile: equal work for every warp, the change of orders is
 //    uniform across the warp (the e^{i m phi} factors of the second walk are computed there, with no
 //    divergence), and warps only meet at the tile boundaries.
-//  * The 8 lanes of a duo are combined every two steps by a transposed reduction (7 exchanges for 8 sums);
+//  * The 8 lanes of a duo are combined every two steps by a transposed reduction (7 exchanges for 8 sums, lane
+//    roles chosen so that nothing has to be selected, run one iteration late under the next one's arithmetic);
 //    each lane then owns one accumulator in shared memory.
 //  * The next tile is prepared WHILE this one is contracted (two tile buffers) by four PRODUCER warps of the
 //    same CTA: warps 4-5 walk the disc-weight recursion of one point per thread -- the reference's exact
 //    operation order, as points_prepare_kernel -- and warps 6-7 write the per-point rows (cos theta, u, phi,
-//    e^{i phi}, u^(8k)); both are latency-bound and short, and then sleep at the tile's single barrier.  The
-//    register file is split to match (setmaxnreg): 216 registers per contraction thread, 40 per producer.
+//    e^{i phi}, u^(8k)); both are latency-bound and short.  Named barriers hand the buffers over ("tile ready"
+//    per contraction warp, "buffer free" per buffer), so the contraction warps never wait for one another.
+//    The register file is split to match (setmaxnreg): 216 registers per contraction thread, 40 per producer.
 //  * e^{i m phi} of the ROUNDED product m phi (what the reference's exp(1j m phi) sees) costs one short
 //    sincos per (point, duo) -- Cody-Waite + Taylor, coefficients in the constant bank -- and one rotation by
 //    e^{i phi} for the duo's second order, with the rounding difference of the two products applied exactly.
@@ -712,6 +718,16 @@ __device__ __forceinline__ void aux_column(double* col, const PointParams& q, co
   }
 }
 
+__device__ __forceinline__ void pf_bar_sync(const int id, const int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void pf_bar_arrive(const int id, const int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+// named barriers: 1 producers only; 2 + 2 w + parity "tile ready" for contraction warp w (128 producer arrivals +
+// the warp's 32); 10 + parity "buffer free" (128 contraction arrivals + the 128 producers)
+constexpr int PF_BAR_PROD = 1, PF_BAR_FULL = 2, PF_BAR_EMPTY = 10;
+
 // SAFE = false: the kernel as described.  SAFE = true: the same walk with the general-purpose cos / sincos for
 // every angle, one CTA per SM and no register hand-over (ptxas 12.9 does not survive a device-function call
 // under setmaxnreg); it is launched after the fast kernel on every call and returns at once unless that one met
@@ -744,7 +760,9 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
   if (warp >= 4) {
     // ---- producers: tile tb + 1 into the other buffer while the contraction warps work on tile tb ----
     if (!SAFE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PF_REGS_PROD));
-    const int pt = tid - 128;
+    // the recursion's fp64 work loads the two SM sub-partitions its warps sit on: the second half of the grid (the
+    // CTAs that usually share an SM with the first half) puts it on the other two
+    const int pt = (tid - 128) ^ ((blockIdx.x * 2 >= gridDim.x) ? 64 : 0);
     const int pcol = pt & 63;
     for (int i = pt; i <= L; i += 128) {
       dc_s[2 * i] = __ldg(q.dc1 + i);
@@ -752,11 +770,14 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
     }
     for (int i = pt; i < 2 * TILE; i += 128)           // the step past LMAX of an odd walk reads zeros
       tiles[(size_t)(i / TILE) * tile_doubles + (size_t)(L + 1) * TILE + (i % TILE)] = 0.0;
-    asm volatile("bar.sync 1, 128;" ::: "memory");     // dc_s is in place (producers only)
-    for (long long tb = tile0; tb <= tile1; ++tb) {
-      // pass tb prepares tile tb (the first pass before any contraction, the last one has nothing to prepare)
+    pf_bar_sync(PF_BAR_PROD, 128);                     // dc_s is in place (producers only)
+    for (long long tb = tile0; tb < tile1 + 2; ++tb) {
+      const int par = (int)(tb - tile0) & 1;
+      // the buffer is free once every contraction warp is done with tile tb - 2 (the passes past the last tile
+      // only match those arrivals)
+      if (tb >= tile0 + 2) pf_bar_sync(PF_BAR_EMPTY + par, 256);
       if (tb < tile1) {
-        double* tn = tiles + (size_t)((int)(tb - tile0) & 1) * tile_doubles;
+        double* tn = tiles + (size_t)par * tile_doubles;
         const long long p = tb * TILE + pcol;
         if (pt < 64) {
           DiscChain ch;
@@ -775,6 +796,8 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
         } else {
           aux_column<SAFE>(tn + aux_off + pcol, q, p, m0);
         }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) pf_bar_arrive(PF_BAR_FULL + 2 * w + par, 160);     // tile tb is complete
         // the inputs of the tile after towards L2
         const long long pn = p + TILE;
         if (tb + 1 < tile1 && pn < q.npts) {
@@ -789,7 +812,6 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
           }
         }
       }
-      __syncthreads();     // tile tb is complete / the contraction warps are done with tile tb - 1
     }
     return;
   }
@@ -806,8 +828,9 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
   const int acc_lane = (b0 ? 16 : 0) + grp * 4 + (b2 ? 2 : 0) + (b1 ? 1 : 0);
 
   for (long long tb = tile0; tb < tile1; ++tb) {
-    __syncthreads();       // this tile's buffer is complete, and every warp is done with the other one
     const int cur = (int)(tb - tile0) & 1;
+    pf_bar_sync(PF_BAR_FULL + 2 * warp + cur, 160);    // this tile's buffer is complete (the warps do not wait
+                                                       // for one another: only the producers see all of them)
     const double* tile = tiles + (size_t)cur * tile_doubles;
     const double* aux = tile + aux_off;
 
@@ -950,8 +973,8 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
       }
       row0 += n2;
     }
+    pf_bar_arrive(PF_BAR_EMPTY + cur, 256);            // this warp is done with the buffer
   }
-  __syncthreads();       // matches the producers' last pass
   __syncwarp();
   // this CTA's partial sums: the (l >= m) entries of the two walks
   double* slot = q.slots + ((size_t)blockIdx.x * q.nbatch + t) * 2 * (L + 1) * (q.mmax + 1);
@@ -970,48 +993,45 @@ __global__ void __launch_bounds__(PF_NT, SAFE ? 1 : 2) points_fused_kernel(const
   }
 }
 
-// grid (lmax+1, nbatch), 1024 threads: out = dfactor[l] * sum over CTA partials.  Sixteen interleaved
+// grid (lmax+1, nbatch, 2), 1024 threads: out = dfactor[l] * sum over CTA partials (z: cosine / sine sums).  Sixteen interleaved
 // partial sums per (l, m) keep independent loads in flight; they are combined in a fixed order.
 constexpr int PR_GROUPS = 16;
 __global__ void __launch_bounds__(64 * PR_GROUPS) points_reduce_kernel(const PointParams q,
                                                                        const __grid_constant__ DegreeFactors dfs) {
-  __shared__ double part[2][PR_GROUPS][64];
-  const int l = blockIdx.x, t = blockIdx.y;
+  __shared__ double part[PR_GROUPS][64];
+  const int l = blockIdx.x, t = blockIdx.y, comp = blockIdx.z;      // comp 0: cosine sums, 1: sine sums
   const int ncol = q.mmax + 1;
   const size_t plane = (size_t)(q.lmax + 1) * ncol;
   const double df = (dfs.dev != nullptr) ? dfs.dev[l] : dfs.v[l];
   const int ml = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  double* out = comp ? q.slm : q.clm;
   for (int m0 = 0; m0 < ncol; m0 += 64) {
     const int m = m0 + ml;
-    double c = 0.0, s = 0.0;
+    double c = 0.0;
     if (m <= l && m < ncol) {
-#pragma unroll 4
-      for (int k = grp; k < q.ncta_p; k += PR_GROUPS) {
-        const double* slot = q.slots + ((size_t)k * q.nbatch + t) * 2 * plane;
-        c += slot[(size_t)l * ncol + m];
-        s += slot[plane + (size_t)l * ncol + m];
-      }
+      const double* src = q.slots + (size_t)t * 2 * plane + (size_t)comp * plane + (size_t)l * ncol + m;
+      const size_t kstride = (size_t)q.nbatch * 2 * plane;
+#pragma unroll 8
+      for (int k = grp; k < q.ncta_p; k += PR_GROUPS) c += src[(size_t)k * kstride];
     }
-    part[0][grp][ml] = c;
-    part[1][grp][ml] = s;
+    part[grp][ml] = c;
     __syncthreads();
-    if (grp < 2 && m < ncol) {
-      // group 0 finishes the cosine sums, group 1 the sine sums: fixed pairwise tree
+    if (grp == 0 && m < ncol) {
+      // fixed pairwise tree over the groups
       double v[PR_GROUPS];
 #pragma unroll
-      for (int j = 0; j < PR_GROUPS; ++j) v[j] = part[grp][j][ml];
+      for (int j = 0; j < PR_GROUPS; ++j) v[j] = part[j][ml];
 #pragma unroll
       for (int w = 1; w < PR_GROUPS; w *= 2) {
 #pragma unroll
         for (int j = 0; j < PR_GROUPS; j += 2 * w) v[j] += v[j + w];
       }
-      const size_t o = ((size_t)t * (q.lmax + 1) + l) * ncol + m;
       double r = 0.0;
       if (m <= l) {
         r = v[0] * df;
         if (q.scale != nullptr) r *= __ldg(q.scale + (size_t)l * q.Mpad + m);
       }
-      if (grp == 0) q.clm[o] = r; else q.slm[o] = r;
+      out[((size_t)t * (q.lmax + 1) + l) * ncol + m] = r;
     }
     __syncthreads();
   }
@@ -1283,7 +1303,7 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
       points_fused_kernel<true><<<grid, PF_NT, smem_fused, st>>>(q);     // returns at once unless flagged
       g_launches.fetch_add(2);
       MHB_CUDA(cudaGetLastError());
-      dim3 rgrid(lmax + 1, nbatch);
+      dim3 rgrid(lmax + 1, nbatch, 2);
       points_reduce_kernel<<<rgrid, 64 * PR_GROUPS, 0, st>>>(q, dfs);
       g_launches.fetch_add(1);
       MHB_CUDA(cudaGetLastError());
@@ -1332,7 +1352,7 @@ int mhb200_point_pressure_f64(int device, const double* P, const double* G, int6
     MHB_CUDA(cudaGetLastError());
   }
   {
-    dim3 grid(lmax + 1, nbatch);
+    dim3 grid(lmax + 1, nbatch, 2);
     points_reduce_kernel<<<grid, 64 * PR_GROUPS, 0, st>>>(q, dfs);
     g_launches.fetch_add(1);
     MHB_CUDA(cudaGetLastError());

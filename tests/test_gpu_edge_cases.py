@@ -76,6 +76,29 @@ def test_points_boundary_sizes(n, L, M):
     assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
 
 
+@pytest.mark.parametrize('n,L,M', [(4097, 60, None), (1000, 61, 40), (129, 33, 33), (70000, 60, 60), (63, 7, 5)])
+def test_points_fused_and_staged_kernels_agree(monkeypatch, n, L, M):
+    """The fused kernel (one launch, one-multiplier recursion, in-kernel weights and trig factors; default for
+    LMAX <= 61) against the round-1 prepare + contract kernels (MHB200_POINTS_FUSED=0), both against the oracle."""
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    P, G, R, lon, lat, AREA = syn.point_cloud(n, seed=3 * n + L, pole_points=True)
+    kw = dict(AREA=AREA, LMAX=L, MMAX=M, LOVE=syn.love_numbers(L))
+    ref = stokes_oracle.gen_point_pressure(P, G, R, lon, lat, **kw) if n <= 5000 else None
+    out = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('MHB200_POINTS_FUSED', flag)
+        out[flag] = mh.gen_point_pressure(P, G, R, lon, lat, **kw)
+        if ref is not None:
+            assert rel_to_max(out[flag].clm, out[flag].slm, ref.clm, ref.slm) <= TOL
+    monkeypatch.delenv('MHB200_POINTS_FUSED')
+    assert rel_to_max(out['0'].clm, out['0'].slm, out['1'].clm, out['1'].slm) <= 1e-13
+    assert np.abs(out['0'].clm - out['1'].clm).max() > 0.0        # the two paths really are different code
+    # bitwise repeatable
+    again = mh.gen_point_pressure(P, G, R, lon, lat, **kw)
+    assert np.array_equal(again.clm, out['1'].clm) and np.array_equal(again.slm, out['1'].slm)
+
+
 def test_points_huge_angles_take_the_safe_kernel():
     """Longitudes / colatitudes far outside a circle (|m phi| beyond the fused kernel's short sincos) are redone by
     the general-purpose variant of the same kernel: still the reference's exp(1j m phi) of the rounded product."""
