@@ -99,6 +99,35 @@ def test_points_fused_and_staged_kernels_agree(monkeypatch, n, L, M):
     assert np.array_equal(again.clm, out['1'].clm) and np.array_equal(again.slm, out['1'].slm)
 
 
+@pytest.mark.parametrize('n', [64, 65, 6400, 100000])
+def test_points_fused_kernel_is_bitwise_repeatable(n):
+    """The fused kernel hands its tile buffers over with named barriers between producer and contraction warps; a
+    missed hand-over would show as run-to-run differences.  Sixty calls, device-resident, must agree bit for bit."""
+    import torch
+    mh, syn = _mh(), _syn()
+    P, G, R, lon, lat, AREA = syn.point_cloud(n, seed=n)
+    dv = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (P, G, R, lon, lat, AREA)]
+    kw = dict(AREA=dv[5], LMAX=60, LOVE=syn.love_numbers(60), as_numpy=False)
+    c0, s0 = mh.point_pressure_batch(dv[0][None], dv[1], dv[2], dv[3], dv[4], **kw)
+    c0, s0 = c0.clone(), s0.clone()
+    for _ in range(60):
+        c, s = mh.point_pressure_batch(dv[0][None], dv[1], dv[2], dv[3], dv[4], **kw)
+        assert torch.equal(c, c0) and torch.equal(s, s0)
+
+
+def test_points_many_turns_of_longitude_stay_exact():
+    """Longitudes a thousand turns away: m phi ~ 4e5 is still inside the fused kernel's short sincos (Cody-Waite with
+    k < 2^19); the result must follow the reference's exp(1j m phi) of the rounded product."""
+    from oracle import stokes_oracle
+    mh, syn = _mh(), _syn()
+    P, G, R, lon, lat, AREA = syn.point_cloud(900, seed=11)
+    lon = lon - 360.0 * 1000.0
+    kw = dict(AREA=AREA, LMAX=60, MMAX=None, LOVE=syn.love_numbers(60))
+    A = mh.gen_point_pressure(P, G, R, lon, lat, **kw)
+    B = stokes_oracle.gen_point_pressure(P, G, R, lon, lat, **kw)
+    assert rel_to_max(A.clm, A.slm, B.clm, B.slm) <= TOL
+
+
 def test_points_huge_angles_take_the_safe_kernel():
     """Longitudes / colatitudes far outside a circle (|m phi| beyond the fused kernel's short sincos) are redone by
     the general-purpose variant of the same kernel: still the reference's exp(1j m phi) of the rounded product."""
