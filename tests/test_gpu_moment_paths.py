@@ -184,11 +184,16 @@ def test_two_threads_two_streams_share_one_plan():
              for i in range(2)]
     ge = torch.from_numpy(geoid).cuda()
     akw = dict(LMAX=L, ELLIPSOID='WGS84', GEOID=ge, LOVE=LOVE, as_numpy=False)
+    pts = [[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in syn.point_cloud(3000 + 500 * i, seed=70 + i)]
+           for i in range(2)]
 
     def work(i):
         a = mh.pressure_stokes_batch(P[i], Gd, Rd, lon, lat, LMAX=L, LOVE=LOVE, as_numpy=False)
         b = mh.atmosphere_stokes_batch(cubes[i][0][None], cubes[i][1][None], lon, lat, **akw)
-        return [x.clone() for x in a + b]
+        pp = pts[i]
+        c = mh.point_pressure_batch(pp[0][None], pp[1], pp[2], pp[3], pp[4], AREA=pp[5], LMAX=L, LOVE=LOVE,
+                                    as_numpy=False)
+        return [x.clone() for x in a + b + c]
 
     want = [work(0), work(1)]                      # single-threaded, default stream
     torch.cuda.synchronize()
