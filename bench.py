@@ -11,7 +11,8 @@ arithmetic (BASELINE.json configs[2]/[4]; the configuration the north star's tar
 on).  A step is one pass of the hot path over a batch of --fields fields per GPU, each derived
 on load from one device-resident base cube by the IEEE-exact scalings of SURVEY.md 8(d)
 (GPH_t = GPH_0 (1+a_t), dP_t = dP_0 (1+b_t)); with N > 1 every rank takes its own time steps
-(weak scaling) and the step ends with the NCCL gather of the coefficient blocks.
+(weak scaling, no collective on the data path: SURVEY.md 8e); the coefficient blocks of the K timed steps
+are gathered by ONE NCCL all-gather at the end, inside the timed region.
 
 value   : whole-job fields/s with inputs resident in HBM (CUDA events, max over ranks); the --fields
           fields of a step are DISTINCT cubes (8 x 615 MB), so every byte comes from DRAM.
@@ -140,7 +141,9 @@ def workload_config(args, cores=None):
             'input_dtype': 'f64',
             'l2_policy': 'inputs exceed L2: %d distinct device-resident cubes per step, 615 MB each, vs 126 MB of L2'
                          % args.fields,
-            'parallelism': 'time-sharded x%d' % args.gpus}
+            'parallelism': 'time-sharded x%d' % args.gpus,
+            'collective': ('none on the data path; one all_gather_into_tensor of the timed steps\' coefficient '
+                           'blocks at the end, inside the timed region') if args.gpus > 1 else None}
 
 
 # ------------------------------------------------------------------------------------------
@@ -321,9 +324,13 @@ def run_cuda_arm(args):
 
     def step():
         clm, slm = mh.atmosphere_stokes_batch(g8, d8, lon, lat, as_numpy=False, **kw)
-        blk = torch.stack([clm, slm], dim=1)
+        return torch.stack([clm, slm], dim=1)
+
+    def collect(blocks):
+        # the only collective: one gather of every step's (T, 2, L+1, M+1) block, at the end of the job
+        blk = torch.cat(blocks, dim=0)
         if world > 1:
-            blk = batch.gather_coefficients(blk, world * T)      # the only collective: final gather
+            blk = batch.gather_coefficients(blk, world * blk.shape[0])
         return blk
 
     def barrier():
@@ -333,13 +340,14 @@ def run_cuda_arm(args):
 
     for _ in range(max(args.warmup, 3)):
         out = step()
+    for _ in range(2):
+        collect([out] * args.steps)       # the gather at the size the timed region uses (NCCL sets up per size)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         sampler.wait_first_row()
     # every rank keeps its GPU under the same load while nvidia-smi takes its first samples
-    # (step() contains the collective, so all ranks must run the same number of steps)
     for _ in range(20):
         out = step()
     torch.cuda.synchronize()
@@ -349,8 +357,8 @@ def run_cuda_arm(args):
     barrier()
     t_begin = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        out = step()
+    outs = [step() for _ in range(args.steps)]
+    gathered = collect(outs)
     e1.record()
     barrier()
     t_end = time.perf_counter()
@@ -361,15 +369,21 @@ def run_cuda_arm(args):
     ring_ms = L.mhb200_profile_mean_ms(ctypes.byref(nrec))
     L.mhb200_profile_enable(0)
     clocks = sampler.stop(t_begin, t_end) if sampler else None
+    per_rank = None
     if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+        # every rank's own device time and dominant-kernel time (the max over ranks is the job's)
+        mine = torch.tensor([ms / args.steps, ring_ms], dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {'ms_per_step': [round(float(v), 4) for v in allr[:, 0]],
+                    'kernel_ms': [round(float(v), 4) for v in allr[:, 1]]}
+        ms = float(allr[:, 0].max().item()) * args.steps
     value = world * T * args.steps / (ms * 1e-3)
     # parity of what was timed, against committed reference-generated goldens (rank 0 holds t = 0 and 7)
     spot = {}
     if rank == 0:
-        res = out.cpu().numpy()
+        res = outs[-1].cpu().numpy()
+        assert gathered.shape[0] == world * T * args.steps
         for t in (0, 7):
             if t < T:
                 spot['t%d' % t] = golden_error(np, res[t, 0], res[t, 1], 'atmosphere_c5_t%d' % t)
@@ -475,7 +489,7 @@ def run_cuda_arm(args):
 
     line = {
         'metric': 'fields_to_stokes_per_second', 'value': value, 'unit': 'fields/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'per_rank': per_rank,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args),
         'e2e': {'value': e2e_value, 'unit': 'fields/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
