@@ -99,6 +99,37 @@ def test_points_fused_and_staged_kernels_agree(monkeypatch, n, L, M):
     assert np.array_equal(again.clm, out['1'].clm) and np.array_equal(again.slm, out['1'].slm)
 
 
+def test_points_randomised_differential_fused_vs_staged(monkeypatch):
+    """Forty random point problems (count from 1 to a few thousand, LMAX 0..61, MMAX, batch size, scalar or
+    per-point G / R, poles included) through the fused kernel and through the prepare + contract kernels: two
+    independent implementations of the same sums must agree to rounding, field by field."""
+    mh, syn = _mh(), _syn()
+    rng = np.random.default_rng(4242)
+    worst = 0.0
+    for case in range(40):
+        n = int(rng.choice([1, 2, 63, 64, 65, 127, 129, int(rng.integers(3, 6000))]))
+        L = int(rng.integers(0, 62))
+        M = None if rng.uniform() < 0.5 else int(rng.integers(0, L + 1))
+        T = int(rng.integers(1, 5))
+        P, G, R, lon, lat, AREA = syn.point_cloud(n, seed=9000 + case, pole_points=bool(rng.uniform() < 0.5))
+        Pb = np.stack([P * (1.0 + 0.1 * t) + 3.0 * t for t in range(T)])
+        if rng.uniform() < 0.3:
+            G = float(np.mean(G))                  # scalar operands broadcast (reference: G.flatten() of a scalar)
+        kw = dict(AREA=AREA, LMAX=L, MMAX=M, LOVE=syn.love_numbers(L))
+        out = {}
+        for flag in ('1', '0'):
+            monkeypatch.setenv('MHB200_POINTS_FUSED', flag)
+            out[flag] = mh.point_pressure_batch(Pb, G, R, lon, lat, **kw)
+        for t in range(T):
+            a, b = out['1'], out['0']
+            scale = max(np.abs(b[0][t]).max(), np.abs(b[1][t]).max())
+            e = max(np.abs(a[0][t] - b[0][t]).max(), np.abs(a[1][t] - b[1][t]).max()) / scale
+            worst = max(worst, e)
+            assert e <= 1e-13, (case, t, n, L, M, e)
+    monkeypatch.delenv('MHB200_POINTS_FUSED')
+    print('randomised point differential test: worst relative-to-max difference %.2e' % worst)
+
+
 @pytest.mark.parametrize('n', [64, 65, 6400, 100000])
 def test_points_fused_kernel_is_bitwise_repeatable(n):
     """The fused kernel hands its tile buffers over with named barriers between producer and contraction warps; a
