@@ -235,6 +235,9 @@ int mhb200_moment_schedule_probe(int nb, int nrings, int nchunks, int max_ctas, 
 int mhb200_moment_layout_probe(int nf, const int* sets, int* col_grid, int* box_start, int* dir,
                                int max_chunks);
 
+/* test hook: the fused point kernel's short sincos (Cody-Waite + Taylor, |a| < 5e5) on n device values */
+int mhb200_sincos_probe(int device, const double* a, int64_t n, double* sin_out, double* cos_out, void* stream);
+
 /* counters for bench.py: kernels launched by this library since load (all threads) */
 uint64_t mhb200_launch_count(void);
 

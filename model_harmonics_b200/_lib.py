@@ -59,6 +59,7 @@ PROTOTYPES = {
     'mhb200_moment_schedule_probe': (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 3 +
                                      [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     'mhb200_moment_layout_probe': (ctypes.c_int, [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 4 + [ctypes.c_int]),
+    'mhb200_sincos_probe': (ctypes.c_int, [ctypes.c_int, _vp, ctypes.c_int64, _vp, _vp, _vp]),
     'mhb200_points_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'mhb200_point_pressure_f64': (ctypes.c_int, [ctypes.c_int, _vp, _vp, ctypes.c_int64, _vp, ctypes.c_int64,
                                                  _vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,

@@ -146,6 +146,34 @@ def test_points_fused_kernel_is_bitwise_repeatable(n):
         assert torch.equal(c, c0) and torch.equal(s, s0)
 
 
+def test_short_sincos_of_the_fused_point_kernel_is_within_two_ulp():
+    """The fused kernel's own sincos (Cody-Waite with a three-part pi/2, Taylor polynomials) against NumPy's on
+    two million arguments up to its range limit: quadrant boundaries, tiny and huge-ish arguments included."""
+    import torch
+    from model_harmonics_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(7)
+    a = np.concatenate([rng.uniform(-7.0, 7.0, 500000), rng.uniform(-400.0, 400.0, 500000),
+                        rng.uniform(-4.9e5, 4.9e5, 900000),
+                        (np.arange(-50000, 50000) * (np.pi / 4)) * (1.0 + 1e-16 * rng.integers(-4, 5, 100000)),
+                        np.array([0.0, -0.0, 1e-300, -1e-300, 1e-8, 4.99e5, -4.99e5])])
+    at = torch.from_numpy(a).cuda()
+    st, ct = torch.empty_like(at), torch.empty_like(at)
+    rc = L.mhb200_sincos_probe(0, at.data_ptr(), a.size, st.data_ptr(), ct.data_ptr(), None)
+    _lib.check(rc, 'mhb200_sincos_probe')
+    torch.cuda.synchronize()
+    s, c = st.cpu().numpy(), ct.cpu().numpy()
+    es = np.abs(s - np.sin(a)) / np.spacing(np.maximum(np.abs(np.sin(a)), 1e-300))
+    ec = np.abs(c - np.cos(a)) / np.spacing(np.maximum(np.abs(np.cos(a)), 1e-300))
+    # near a zero of sin / cos the error is bounded absolutely (the reduction carries ~1e-17), not in ulps of the result
+    ok_s = (es <= 2.0) | (np.abs(s - np.sin(a)) <= 2e-16)
+    ok_c = (ec <= 2.0) | (np.abs(c - np.cos(a)) <= 2e-16)
+    assert ok_s.all() and ok_c.all(), (float(es[~ok_s].max()) if (~ok_s).any() else 0.0,
+                                       float(ec[~ok_c].max()) if (~ok_c).any() else 0.0)
+    print('short sincos: max error %.2f / %.2f ulp where the result is not near zero' % (
+        es[np.abs(np.sin(a)) > 0.1].max(), ec[np.abs(np.cos(a)) > 0.1].max()))
+
+
 def test_points_many_turns_of_longitude_stay_exact():
     """Longitudes a thousand turns away: m phi ~ 4e5 is still inside the fused kernel's short sincos (Cody-Waite with
     k < 2^19); the result must follow the reference's exp(1j m phi) of the rounded product."""
