@@ -804,7 +804,9 @@ __device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive 
 __global__ void __launch_bounds__(256, 2) legendre_moment_kernel(const __grid_constant__ LegParams q) {
   if (*reinterpret_cast<const volatile int*>(q.flag) != 0) return;
   __shared__ double tile[2][32 * 64];
-  const int unit = blockIdx.x, tt = blockIdx.y / q.nsplit, split = blockIdx.y % q.nsplit;
+  // grid (field x split, unit): CTAs are handed out x-fastest, so every field's longest units (low orders: up to
+  // four times the tiles of the high ones) start first and the short ones fill the tail
+  const int unit = blockIdx.y, tt = blockIdx.x / q.nsplit, split = blockIdx.x % q.nsplit;
   const int lb = q.unit_lm[2 * unit], m = q.unit_lm[2 * unit + 1];
   const int lbase = lb * LBLK, lend = min(lbase + LBLK - 1, q.lmax);
   const int sb = q.field_slot[tt], se = q.field_slot[tt + 1];
@@ -1459,7 +1461,7 @@ static int moment_reduce(mhb200_plan* pl, const MomWs& lay, char* ws, int nb, co
   for (int i = 0; i <= nb; ++i) q.field_slot[i] = field_slot[i];
   q.G = (double*)(ws + lay.G);
   q.flag = (const int*)(ws + lay.flag);
-  legendre_moment_kernel<<<dim3(mp->nunits, nb * nsplit), 256, 0, st>>>(q);
+  legendre_moment_kernel<<<dim3(nb * nsplit, mp->nunits), 256, 0, st>>>(q);
   g_launches.fetch_add(1);
   MHB_CUDA(cudaGetLastError());
   FinParams f;
